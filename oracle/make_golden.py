@@ -1,0 +1,105 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on seeded inputs.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (where /root/reference is mounted):
+
+    python -m oracle.make_golden
+
+/root/reference does not exist on the GPU box, so the outputs are committed as small fixtures.
+The reference module imports cvxpy at module scope (sparse_sensing.py:15) but the hot path only
+touches cp.multiply(a, b) + c -> .value (sparse_sensing.py:233-238); cvxpy is not installed here,
+so a minimal stand-in exposing just that is put on sys.path (it changes no reference code).
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+
+def _import_reference():
+    try:
+        import cvxpy  # noqa: F401
+    except ImportError:
+        shim = types.ModuleType("cvxpy")
+
+        class _Expr:
+            def __init__(self, v):
+                self.value = np.asarray(v)
+
+            def __add__(self, o):
+                return _Expr(self.value + (o.value if isinstance(o, _Expr) else o))
+
+            __radd__ = __add__
+
+        shim.multiply = lambda a, b: _Expr(np.asarray(a) * np.asarray(b))
+        sys.modules["cvxpy"] = shim
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, os.path.join(REF, "src"))
+    import openmeasure.sparse_sensing as sps
+    return sps
+
+
+def _case(sps, name, X, F, n_modes, select_modes="number", scale_type="std", axis_cnt=1,
+          n_meas=3, sigma=0.0, rng=None):
+    n, m = X.shape
+    n_c = n // F
+    xyz = np.zeros((n_c, 3))
+    spr = sps.SPR(X.copy(), F, xyz)
+    spr.fit(scale_type=scale_type, axis_cnt=axis_cnt, select_modes=select_modes, n_modes=n_modes)
+    Ur0 = spr.Ur.copy()
+    C = spr.optimal_placement()
+    piv = np.argmax(C, axis=1).astype(np.int64)
+    spr.train(C)
+    ys = []
+    for t in range(n_meas):
+        x_new = X[:, t % m] * (1.0 + 0.01 * rng.standard_normal(n))
+        y = np.zeros((len(piv), 3))
+        y[:, 0] = x_new[piv]
+        y[:, 1] = sigma * np.abs(y[:, 0]) if sigma else 0.0
+        y[:, 2] = piv // n_c
+        ys.append(y)
+    Ar_p, Ar_sig = spr.predict(ys)
+    Xrec = spr.reconstruct(Ar_p)
+    out = dict(
+        X=X, F=np.int64(F), n_modes=np.float64(n_modes), select_modes=select_modes,
+        scale_type=scale_type, axis_cnt=np.int64(-1 if axis_cnt is None else axis_cnt),
+        X_cnt=spr.X_cnt, X_scl=spr.X_scl, r=np.int64(spr.r), Sigma_r=spr.Sigma_r,
+        Ur=Ur0, Ar=spr.Ar, Vr=spr.Vr, piv=piv, Theta=spr.Theta,
+        Y=np.stack(ys), Ar_pred=Ar_p, Ar_sigma=Ar_sig, X_rec=Xrec,
+        X0_checksum=np.array([spr.X0.sum(), np.abs(spr.X0).sum()]),
+        X0_head=spr.X0[: min(n, 64)].copy(),
+    )
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: n={n} m={m} r={spr.r} piv[:6]={piv[:6]} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
+def main():
+    sps = _import_reference()
+    sys.path.insert(0, ROOT)
+    from oracle import synth
+    os.makedirs(GOLD, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+
+    # g1: the reference unit tests' own shape (tests/test_rom.py:8-13: 2 features x 10 points x 5)
+    _case(sps, "g1_unit_20x5", rng.random((20, 5)), 2, 4, rng=rng)
+    # g2: random 3 features x 400 cells x 12 snapshots, variance-based rank, pareto scaling
+    _case(sps, "g2_rand_1200x12_pareto", rng.random((1200, 12)) + 0.5, 3, 95.0,
+          select_modes="variance", scale_type="pareto", rng=rng)
+    # g3: synthetic generator, README-like layout (9 features), scaled down: 9 x 400 x 41, r = 14
+    _case(sps, "g3_synth_3600x41_r14", synth.snapshots(9, 400, 41, 14), 9, 14, rng=rng)
+    # g4: range scaling, scalar centring (axis_cnt=None), weighted measurements (sigma != 0)
+    _case(sps, "g4_synth_2400x24_range", synth.snapshots(4, 600, 24, 10), 4, 10,
+          scale_type="range", axis_cnt=None, sigma=0.02, rng=rng)
+    # g5: wider snapshot set, m > 128 exercises the multi-leaf row-mean tree: 2 x 300 x 160, r = 20
+    _case(sps, "g5_synth_600x160_r20", synth.snapshots(2, 300, 160, 20), 2, 20, rng=rng)
+
+
+if __name__ == "__main__":
+    main()
