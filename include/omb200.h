@@ -1,0 +1,134 @@
+/*
+ * omb200.h -- C ABI of libomb200.so: the B200 (sm_100a) snapshot-POD sparse-sensing hot path.
+ *
+ * The reference (OpenMEASURE v0.3.8) is pure Python and has NO FFI of its own: its hot path calls
+ * numpy/scipy (OpenBLAS/LAPACK) directly from src/openmeasure/sparse_sensing.py.  Each entry point
+ * below therefore cites the reference call site whose library routine it replaces; the Python
+ * mirror of the reference classes (openmeasure_b200/sparse_sensing.py: ROM, SPR) binds them through
+ * ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a host pointer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all calls are
+ *     asynchronous on it unless stated, and never allocate device memory (workspaces are
+ *     caller-provided, sized by the *_ws_bytes queries);
+ *   - return value: 0 ok, <0 invalid argument, >0 cudaError_t; omb_last_error() gives the text;
+ *   - snapshot layout: X is (F * n_c) x m, C-order FP64 (row = m contiguous snapshots), feature
+ *     block f = rows [f*n_c, (f+1)*n_c)  (sparse_sensing.py:110);
+ *   - basis layout: "mode-major" Ut is r x ld (ld >= n, ld % 2 == 0), Ut[q*ld + i] = U_r[i, q],
+ *     so that the n candidate locations are the coalesced axis of every placement kernel.
+ */
+#ifndef OMB200_H
+#define OMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------------------------- */
+int omb_version(void);
+const char* omb_last_error(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py's
+ * gpu_launches claim is read from here, not estimated) */
+int64_t omb_launch_count(void);
+void omb_launch_count_reset(void);
+
+/* scale_type codes for omb_finalize_scale (sparse_sensing.py:114-161) */
+enum {
+    OMB_SCALE_STD = 0, OMB_SCALE_NONE = 1, OMB_SCALE_PARETO = 2, OMB_SCALE_VAST = 3,
+    OMB_SCALE_RANGE = 4, OMB_SCALE_LEVEL = 5, OMB_SCALE_MAX = 6, OMB_SCALE_VARIANCE = 7,
+    OMB_SCALE_POISSON = 8, OMB_SCALE_L2NORM = 9
+};
+
+/* ---- synthetic snapshots (no reference counterpart; DESIGN.md "Synthetic workload") -------- */
+int omb_synth_fill(double* d_X, int64_t F, int64_t n_cells, int64_t cell0, int64_t ncell_loc,
+                   int64_t m, int64_t K, uint64_t seed, const double* d_amp, const double* d_dec,
+                   double eps, void* stream);
+
+/* ---- K1: centring / scaling statistics (replaces np.average/np.std/np.max/np.min over the
+ *      n_cells-row feature blocks, sparse_sensing.py:112-161) -------------------------------- */
+/* Row means with numpy's pairwise tree (bit-exact): d_cnt[i] = mean(X[i, :]).  rows = F*n_c. */
+int omb_row_means(const double* d_X, int64_t rows, int64_t m, double* d_cnt, void* stream);
+/* Per-feature block reductions with numpy's pairwise tree over the n_c*m contiguous elements:
+ *   mode 0: d_out[f*4 + {0,1,2}] = {sum, min, max}
+ *   mode 1: d_out[f*4 + 3]       = sum((x - d_out[f*4+0]/mean_count)^2)   (np.std's second pass;
+ *           mean_count = elements per block over ALL ranks, d_out[f*4+0] the global block sum)
+ * d_ws: omb_block_stats_ws_bytes(F, n_c*m) bytes. */
+int64_t omb_block_stats_ws_bytes(int64_t F, int64_t block_elems);
+int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems, int mode, int64_t mean_count,
+                    double* d_out, void* d_ws, void* stream);
+/* d_scl[f] from the block statistics (count = GLOBAL elements per block); when axis_cnt is
+ * None (fill_cnt != 0) also fills d_cnt[f*n_c_loc .. ) with the block mean (sparse_sensing.py:112
+ * with axis=None). */
+int omb_finalize_scale(const double* d_stats, int64_t F, int64_t count, int scale_type,
+                       double* d_scl, int fill_cnt, double* d_cnt, int64_t n_c_loc, void* stream);
+/* X0 = (X - cnt) / scl materialised (sparse_sensing.py:169); only used when user code reads .X0 */
+int omb_scale_rows(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
+                   const double* d_scl, double* d_X0, void* stream);
+
+/* x = scl[f(i)] * x0 + cnt[i] for one length-n vector (replaces ROM.unscale_data's
+ * cp.multiply(X_scl, x0) + X_cnt, sparse_sensing.py:235; two roundings like the reference) */
+int omb_unscale(const double* d_x0, const double* d_cnt, const double* d_scl, int64_t n_c, int64_t n,
+                double* d_out, void* stream);
+
+/* ---- K3: POD contraction (replaces the tall-skinny part of np.linalg.svd, sparse_sensing.py:272)
+ * Per-feature Gram of the centred rows: d_Gf[f] (m x m, row-major, full symmetric) =
+ * sum_i (x_i - cnt_i)(x_i - cnt_i)^T over the rows of feature f.  d_cnt may be NULL (no centring).
+ * Deterministic: fixed row split, fixed-order reduction, no atomics.  */
+int64_t omb_gram_ws_bytes(int64_t F, int64_t n_c, int64_t m);
+int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
+             double* d_Gf, void* d_ws, void* stream);
+/* G (m x m) = sum_f Gf[f] / scl[f]^2, fixed order. d_scl may be NULL (all ones). */
+int omb_gram_combine(const double* d_Gf, int64_t F, int64_t m, const double* d_scl, double* d_G,
+                     void* stream);
+
+/* ---- K5: back-projection U_r = X0 * W, W = V_r Sigma_r^-1 (m x r row-major), written mode-major,
+ *      with the initial QRCP column norms vn[i] = ||U_r[i,:]||_2 fused (replaces U = Q*U_R inside
+ *      dgesdd and the dnrm2 initialisation of dgeqp3). d_vn may be NULL. -------------------- */
+int omb_backproject(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
+                    const double* d_scl, const double* d_W, int64_t r, double* d_Ut, int64_t ld,
+                    double* d_vn, void* stream);
+
+/* ---- K6: QR with column pivoting over the n candidate locations (replaces
+ *      scipy.linalg.qr(self.Ur.T, pivoting=True) -> LAPACK dgeqp3/dlaqp2, sparse_sensing.py:739).
+ * d_Ut   r x ld mode-major basis (read only), d_vn initial norms (NULL -> computed here),
+ * d_work r x ld scratch for the trailing matrix, d_ws omb_qrcp_ws_bytes() bytes,
+ * block  = steps between trailing-matrix rewrites (1 = LAPACK's unblocked dlaqp2 arithmetic),
+ * outputs (device): d_piv[s] global row indices in selection order (+ index_base), d_rdiag[s] =
+ * R[k,k], d_gap[s] = relative gap between the best and second-best candidate norm (degeneracy
+ * meter).  `valid` (NULL or n bytes, 0 = excluded) implements optimal_placement(mask=...). */
+int64_t omb_qrcp_ws_bytes(int64_t n, int64_t r);
+int omb_qrcp(const double* d_Ut, int64_t ld, int64_t n, int64_t r, int64_t s, const double* d_vn,
+             double* d_work, void* d_ws, int block, int64_t index_base, int64_t* d_piv,
+             double* d_rdiag, double* d_gap, void* stream);
+
+/* ---- K8/K9: train = row gather (replaces the dense C.dot(Ur), C.dot(X_cnt);
+ *      sparse_sensing.py:797, :573).  d_Theta is s x r row-major, d_cnt_s may be NULL. -------- */
+int omb_gather_rows(const double* d_Ut, int64_t ld, int64_t r, const int64_t* d_piv, int64_t s,
+                    double* d_Theta, const double* d_cnt, double* d_cnt_s, void* stream);
+/* Ur (n x r, C-order) <- Ut, and back (for the .Ur attribute / fit(basis=...) / mask) */
+int omb_modes_to_rows(const double* d_Ut, int64_t ld, int64_t n, int64_t r, double* d_Ur,
+                      void* stream);
+int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, int64_t ld,
+                      double* d_vn, void* stream);
+
+/* ---- K10: batched OLS predict (replaces the per-vector np.linalg.pinv + dot loop,
+ *      sparse_sensing.py:865-878 with all sigma == 0):
+ *      A (N x r) = ((Y - cnt_s) / scl_s) * PinvT,  Y N x s row-major, PinvT s x r row-major ---- */
+int omb_ols_predict(const double* d_Y, const double* d_cnt_s, const double* d_scl_s,
+                    const double* d_PinvT, int64_t N, int64_t s, int64_t r, double* d_A,
+                    void* stream);
+
+/* ---- K11: reconstruct rows [row0, row0+nrows) of X_rec = U_r A^T, unscaled in the epilogue
+ *      out[i, k] = scl[f(i)] * acc + cnt[i]  (replaces Ur @ Ar.T + the per-column unscale_data,
+ *      sparse_sensing.py:371-373, :235).  d_out is nrows x N row-major.  d_cnt/d_scl may be NULL. */
+int omb_reconstruct(const double* d_Ut, int64_t ld, int64_t r, const double* d_A, int64_t N,
+                    const double* d_cnt, const double* d_scl, int64_t n_c, int64_t row0,
+                    int64_t nrows, double* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMB200_H */

@@ -1,0 +1,65 @@
+// common.cuh -- shared helpers for libomb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace omb {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define OMB_CHECK_ARG(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            omb::set_error("%s: invalid argument: %s", __func__, msg); \
+            return -1;                                             \
+        }                                                          \
+    } while (0)
+
+#define OMB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            omb::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__)); \
+            return (int)e__;                                                        \
+        }                                                                           \
+    } while (0)
+
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+int sm_count();
+
+// streaming (evict-first) 128-bit and 64-bit global accesses for data touched once per pass
+__device__ __forceinline__ double2 ldg_stream2(const double* p)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream(const double* p)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream2(double* p, double2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream(double* p, double v)
+{
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8).  SASS: DMMA.8x8x4.
+//   a  = A[lane/4][lane%4],  b = B[lane%4][lane/4],  c0/c1 = C[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+}  // namespace omb

@@ -1,0 +1,206 @@
+// gram.cu -- K3: POD contraction of the tall-skinny snapshot matrix on the FP64 tensor path.
+//
+// Replaces the O(n m^2) part of np.linalg.svd(X0) (reference sparse_sensing.py:272, LAPACK dgesdd):
+// per feature block f, Gf = sum_i (x_i - cnt_i)(x_i - cnt_i)^T over the block's rows, so the
+// scaling 1/scl_f^2 (known only after the statistics pass) is applied to the tiny m x m result
+// and X0 is never materialised.  DMMA.8x8x4 (mma.sync m8n8k4 f64) -- tcgen05 has no FP64 kind.
+// Deterministic: fixed row split per feature, partial tiles reduced in fixed order, no atomics.
+#include "common.cuh"
+#include "../../include/omb200.h"
+
+namespace omb {
+
+constexpr int GT = 64;            // output tile edge
+constexpr int GK = 32;            // rows (contraction) per shared-memory chunk
+constexpr int GLD = GT + 4;       // == 4 (mod 16): conflict-free 64-bit fragment loads
+constexpr int G_THREADS = 128;    // 2 x 2 warps, 32 x 32 outputs each
+
+struct GramPlan {
+    int T;          // tiles per edge
+    int ntiles;     // upper-triangular tile pairs
+    int splits;     // row splits per feature
+    int64_t rows_per_split;
+};
+
+static GramPlan gram_plan(int64_t F, int64_t n_c, int64_t m)
+{
+    GramPlan p;
+    p.T = (int)ceil_div(m, GT);
+    p.ntiles = p.T * (p.T + 1) / 2;
+    int64_t target = (int64_t)sm_count() * 6;                  // CTAs wanted in flight
+    int64_t splits = ceil_div(target, (int64_t)F * p.ntiles);
+    int64_t max_splits = ceil_div(n_c, 4 * GK);                 // at least 4 chunks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 4096) splits = 4096;
+    p.rows_per_split = round_up(ceil_div(n_c, splits), GK);
+    p.splits = (int)ceil_div(n_c, p.rows_per_split);
+    return p;
+}
+
+__device__ __forceinline__ void tile_pair(int t, int T, int& ti, int& tj)
+{
+    // enumerate (ti <= tj) row by row
+    ti = 0;
+    int rowlen = T;
+    while (t >= rowlen) { t -= rowlen; ++ti; --rowlen; }
+    tj = ti + t;
+}
+
+__global__ void __launch_bounds__(G_THREADS)
+gram_tile_kernel(const double* __restrict__ X, int64_t n_c, int m, const double* __restrict__ cnt, int T,
+                 int64_t rows_per_split, int splits, double* __restrict__ part)
+{
+    __shared__ double sA[GK * GLD];
+    __shared__ double sB[GK * GLD];
+    __shared__ double s_cnt[GK];
+
+    int ti, tj;
+    tile_pair(blockIdx.x, T, ti, tj);
+    const int split = blockIdx.y, f = blockIdx.z;
+    const bool diag = (ti == tj);
+    const int64_t row_lo = (int64_t)split * rows_per_split;
+    int64_t row_hi = row_lo + rows_per_split;
+    if (row_hi > n_c) row_hi = n_c;
+    const double* Xf = X + (int64_t)f * n_c * m;
+    const double* cf = cnt ? cnt + (int64_t)f * n_c : nullptr;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ib = (warp >> 1) * 32, jb = (warp & 1) * 32;
+    const int fr = lane & 3, fc = lane >> 2;
+
+    double c[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+
+    const double* sBp = diag ? sA : sB;
+    for (int64_t k0 = row_lo; k0 < row_hi; k0 += GK) {
+        if (threadIdx.x < GK) {
+            int64_t row = k0 + threadIdx.x;
+            s_cnt[threadIdx.x] = (cf && row < row_hi) ? cf[row] : 0.0;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < GK * GT; e += G_THREADS) {
+            const int kr = e / GT, col = e - kr * GT;
+            const int64_t row = k0 + kr;
+            const bool rok = row < row_hi;
+            const int ca = ti * GT + col;
+            double va = 0.0;
+            if (rok && ca < m) va = ldg_stream(Xf + row * m + ca) - s_cnt[kr];
+            sA[kr * GLD + col] = va;
+            if (!diag) {
+                const int cb = tj * GT + col;
+                double vb = 0.0;
+                if (rok && cb < m) vb = ldg_stream(Xf + row * m + cb) - s_cnt[kr];
+                sB[kr * GLD + col] = vb;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < GK / 4; ++k4) {
+            double a[4], b[4];
+            const int base = (k4 * 4 + fr) * GLD + fc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = sA[base + ib + q * 8];
+                b[q] = sBp[base + jb + q * 8];
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dmma884(c[p][q][0], c[p][q][1], a[p], b[q]);
+        }
+        __syncthreads();
+    }
+
+    // partial tile: part[f][split][tile][GT][GT]
+    double* out = part + (((int64_t)f * splits + split) * gridDim.x + blockIdx.x) * (GT * GT);
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ib + p * 8 + fc;
+            const int j = jb + q * 8 + 2 * fr;
+            *reinterpret_cast<double2*>(out + i * GT + j) = make_double2(c[p][q][0], c[p][q][1]);
+        }
+}
+
+// Gf[f][i][j] = sum over splits (fixed order) of the tile holding (min-tile, max-tile); mirrored.
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const double* __restrict__ part, int m, int T, int ntiles, int splits,
+                   double* __restrict__ Gf)
+{
+    const int f = blockIdx.y;
+    const int64_t mm = (int64_t)m * m;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mm;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(e / m), j = (int)(e - (int64_t)i * m);
+        if (i > j) { int t = i; i = j; j = t; }          // read the upper triangle, mirror
+        const int ti = i / GT, tj = j / GT;
+        const int tile = ti * T - ti * (ti - 1) / 2 + (tj - ti);
+        const double* p = part + ((int64_t)f * splits * ntiles + tile) * (GT * GT) + (i % GT) * GT + (j % GT);
+        double s = 0.0;
+        for (int sp = 0; sp < splits; ++sp) s += p[(int64_t)sp * ntiles * (GT * GT)];
+        Gf[(int64_t)f * mm + e] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gram_combine_kernel(const double* __restrict__ Gf, int F, int64_t mm, const double* __restrict__ scl,
+                    double* __restrict__ G)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mm;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int f = 0; f < F; ++f) {
+            double w = 1.0;
+            if (scl) { double sc = scl[f]; w = sc * sc; }
+            s += Gf[(int64_t)f * mm + e] / w;
+        }
+        G[e] = s;
+    }
+}
+
+}  // namespace omb
+
+using namespace omb;
+
+extern "C" int64_t omb_gram_ws_bytes(int64_t F, int64_t n_c, int64_t m)
+{
+    if (F <= 0 || n_c <= 0 || m <= 0) return 0;
+    GramPlan p = gram_plan(F, n_c, m);
+    return (int64_t)sizeof(double) * F * p.splits * p.ntiles * GT * GT;
+}
+
+extern "C" int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
+                        double* d_Gf, void* d_ws, void* stream)
+{
+    OMB_CHECK_ARG(d_X && d_Gf && d_ws, "null pointer");
+    OMB_CHECK_ARG(F > 0 && n_c > 0 && m > 0, "non-positive size");
+    OMB_CHECK_ARG(F <= 65535 && m <= 16384, "F or m too large");
+    GramPlan p = gram_plan(F, n_c, m);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)p.ntiles, (unsigned)p.splits, (unsigned)F);
+    gram_tile_kernel<<<grid, G_THREADS, 0, st>>>(d_X, n_c, (int)m, d_cnt, p.T, p.rows_per_split, p.splits,
+                                                  (double*)d_ws);
+    int rc = check_launch("gram_tile_kernel");
+    if (rc) return rc;
+    int64_t gx = ceil_div(m * m, 256);
+    if (gx > 2048) gx = 2048;
+    dim3 rgrid((unsigned)gx, (unsigned)F);
+    gram_reduce_kernel<<<rgrid, 256, 0, st>>>((const double*)d_ws, (int)m, p.T, p.ntiles, p.splits, d_Gf);
+    return check_launch("gram_reduce_kernel");
+}
+
+extern "C" int omb_gram_combine(const double* d_Gf, int64_t F, int64_t m, const double* d_scl, double* d_G,
+                                void* stream)
+{
+    OMB_CHECK_ARG(d_Gf && d_G, "null pointer");
+    OMB_CHECK_ARG(F > 0 && m > 0, "non-positive size");
+    int64_t gx = ceil_div(m * m, 256);
+    if (gx > 2048) gx = 2048;
+    gram_combine_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(d_Gf, (int)F, m * m, d_scl, d_G);
+    return check_launch("gram_combine_kernel");
+}

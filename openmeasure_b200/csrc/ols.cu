@@ -1,0 +1,269 @@
+// ols.cu -- K8-K11: train (row gather), batched OLS predict, reconstruct with fused unscale,
+// and the layout helpers between the mode-major basis and the reference's (n, r) view.
+//
+//   gather      replaces Theta = C.dot(Ur) and C.dot(X_cnt[:,0]) for a one-hot C
+//               (reference sparse_sensing.py:797, :573): a gather of s rows.
+//   predict     replaces the per-vector loop  pinv(Theta) @ ((y - cnt)/scl)  (:865-878, W = I)
+//               by one (N x s)(s x r) FP64 tensor-core GEMM with the scaling fused on load.
+//   reconstruct replaces X_rec = Ur @ Ar.T followed by the per-column unscale_data (:371-373, :235)
+//               by a row-sharded GEMM whose epilogue is scl*acc + cnt (two roundings, like the
+//               reference's multiply-then-add).
+#include "common.cuh"
+#include "../../include/omb200.h"
+
+namespace omb {
+
+__global__ void gather_rows_kernel(const double* __restrict__ Ut, int64_t ld, int r, const int64_t* __restrict__ piv,
+                                   int s, double* __restrict__ Theta, const double* __restrict__ cnt,
+                                   double* __restrict__ cnt_s)
+{
+    const int total = s * r;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int a = e / r, q = e - a * r;
+        Theta[e] = Ut[(int64_t)q * ld + piv[a]];
+    }
+    if (cnt && cnt_s)
+        for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < s; a += gridDim.x * blockDim.x)
+            cnt_s[a] = cnt[piv[a]];
+}
+
+// Ur[i][q] = Ut[q][i]   (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+modes_to_rows_kernel(const double* __restrict__ Ut, int64_t ld, int64_t n, int r, double* __restrict__ Ur)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    const int64_t ntile_i = ceil_div(n, 32);
+    const int ntile_q = (r + 31) / 32;
+    for (int64_t tI = blockIdx.x; tI < ntile_i * ntile_q; tI += gridDim.x) {
+        const int64_t i0 = (tI / ntile_q) * 32;
+        const int q0 = (int)(tI % ntile_q) * 32;
+        for (int yy = ty; yy < 32; yy += 8) {
+            const int q = q0 + yy;
+            const int64_t i = i0 + tx;
+            tile[yy][tx] = (q < r && i < n) ? Ut[(int64_t)q * ld + i] : 0.0;
+        }
+        __syncthreads();
+        for (int yy = ty; yy < 32; yy += 8) {
+            const int64_t i = i0 + yy;
+            const int q = q0 + tx;
+            if (i < n && q < r) Ur[i * r + q] = tile[tx][yy];
+        }
+        __syncthreads();
+    }
+}
+
+// Ut[q][i] = Ur[i][q]; optional row norms (sequential fma over q, the oracle's dnrm2 order)
+__global__ void __launch_bounds__(256)
+rows_to_modes_kernel(const double* __restrict__ Ur, int64_t n, int r, double* __restrict__ Ut, int64_t ld)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t ntile_i = ceil_div(n, 32);
+    const int ntile_q = (r + 31) / 32;
+    for (int64_t tI = blockIdx.x; tI < ntile_i * ntile_q; tI += gridDim.x) {
+        const int64_t i0 = (tI / ntile_q) * 32;
+        const int q0 = (int)(tI % ntile_q) * 32;
+        for (int yy = ty; yy < 32; yy += 8) {
+            const int64_t i = i0 + yy;
+            const int q = q0 + tx;
+            tile[yy][tx] = (i < n && q < r) ? Ur[i * r + q] : 0.0;
+        }
+        __syncthreads();
+        for (int yy = ty; yy < 32; yy += 8) {
+            const int q = q0 + yy;
+            const int64_t i = i0 + tx;
+            if (q < r && i < n) Ut[(int64_t)q * ld + i] = tile[tx][yy];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+row_norms_kernel(const double* __restrict__ Ut, int64_t ld, int64_t n, int r, double* __restrict__ vn)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < r; ++k) { const double x = Ut[(int64_t)k * ld + j]; s = fma(x, x, s); }
+        vn[j] = sqrt(s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 64 x 64 output tile, 2 x 2 warps of 32 x 32, DMMA.8x8x4, contraction chunks of 32.
+//   MODE 0 (predict):     C[i][j] = sum_k ((Y[i][k] - cs[k]) / ss[k]) * B[k][j]        row-major out
+//   MODE 1 (reconstruct): C[i][j] = scl[f(i)] * (sum_k Ut[k][i] * Ac[j][k]) + cnt[i]   row-major out
+// ---------------------------------------------------------------------------------------------
+constexpr int OT = 64, OK_ = 32, O_THREADS = 128;
+constexpr int O_LD = OT + 4;      // [k][i] operand tiles: fr*LD + fc distinct (mod 16)
+constexpr int O_LDK = OK_ + 4;    // [i][k] operand tiles: fc*LD + fr distinct (mod 16)
+
+template <int MODE>
+__global__ void __launch_bounds__(O_THREADS)
+ols_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, int64_t M, int64_t Nn, int K,
+                int64_t lda, const double* __restrict__ p0, const double* __restrict__ p1, int64_t n_c,
+                int64_t row0, double* __restrict__ out)
+{
+    __shared__ double sA[(MODE == 0) ? OT * O_LDK : OK_ * O_LD];
+    __shared__ double sB[(MODE == 0) ? OK_ * O_LD : OT * O_LDK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane & 3, fc = lane >> 2;
+    const int ib = (warp >> 1) * 32, jb = (warp & 1) * 32;
+    const int64_t tiles_j = ceil_div(Nn, OT);
+    const int64_t tiles = ceil_div(M, OT) * tiles_j;
+
+    for (int64_t tI = blockIdx.x; tI < tiles; tI += gridDim.x) {
+        const int64_t i0 = (tI / tiles_j) * OT, j0 = (tI % tiles_j) * OT;
+        double c[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+
+        for (int k0 = 0; k0 < K; k0 += OK_) {
+            __syncthreads();
+            if (MODE == 0) {
+                // sA[i][k] = (Y[i0+i][k0+k] - cs[k]) / ss[k];  sB[k][j] = PinvT[k0+k][j0+j]
+                for (int e = threadIdx.x; e < OT * OK_; e += O_THREADS) {
+                    const int ii = e / OK_, kk = e - ii * OK_;
+                    const int64_t i = i0 + ii;
+                    const int k = k0 + kk;
+                    double v = 0.0;
+                    if (i < M && k < K) {
+                        v = A[i * lda + k];
+                        if (p0) v = v - p0[k];
+                        if (p1) v = v / p1[k];
+                    }
+                    sA[ii * O_LDK + kk] = v;
+                }
+                for (int e = threadIdx.x; e < OK_ * OT; e += O_THREADS) {
+                    const int kk = e / OT, jj = e - kk * OT;
+                    const int k = k0 + kk;
+                    const int64_t j = j0 + jj;
+                    sB[kk * O_LD + jj] = (k < K && j < Nn) ? B[(int64_t)k * Nn + j] : 0.0;
+                }
+            } else {
+                // sA[k][i] = Ut[k0+k][row0+i0+i];  sB[j][k] = Ac[j0+j][k0+k]
+                for (int e = threadIdx.x; e < OK_ * OT; e += O_THREADS) {
+                    const int kk = e / OT, ii = e - kk * OT;
+                    const int k = k0 + kk;
+                    const int64_t i = i0 + ii;
+                    sA[kk * O_LD + ii] = (k < K && i < M) ? A[(int64_t)k * lda + row0 + i] : 0.0;
+                }
+                for (int e = threadIdx.x; e < OT * OK_; e += O_THREADS) {
+                    const int jj = e / OK_, kk = e - jj * OK_;
+                    const int64_t j = j0 + jj;
+                    const int k = k0 + kk;
+                    sB[jj * O_LDK + kk] = (j < Nn && k < K) ? B[j * K + k] : 0.0;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k4 = 0; k4 < OK_ / 4; ++k4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (MODE == 0) {
+                        a[q] = sA[(ib + q * 8 + fc) * O_LDK + k4 * 4 + fr];
+                        b[q] = sB[(k4 * 4 + fr) * O_LD + jb + q * 8 + fc];
+                    } else {
+                        a[q] = sA[(k4 * 4 + fr) * O_LD + ib + q * 8 + fc];
+                        b[q] = sB[(jb + q * 8 + fc) * O_LDK + k4 * 4 + fr];
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dmma884(c[p][q][0], c[p][q][1], a[p], b[q]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int64_t i = i0 + ib + p * 8 + fc;
+            if (i >= M) continue;
+            double sc = 1.0, cn = 0.0;
+            if (MODE == 1) {
+                if (p1) sc = p1[(row0 + i) / n_c];
+                if (p0) cn = p0[row0 + i];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t j = j0 + jb + q * 8 + 2 * fr + e;
+                    if (j >= Nn) continue;
+                    double v = c[p][q][e];
+                    if (MODE == 1) { v = sc * v; v = v + cn; }
+                    out[i * Nn + j] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace omb
+
+using namespace omb;
+
+extern "C" int omb_gather_rows(const double* d_Ut, int64_t ld, int64_t r, const int64_t* d_piv, int64_t s,
+                               double* d_Theta, const double* d_cnt, double* d_cnt_s, void* stream)
+{
+    OMB_CHECK_ARG(d_Ut && d_piv && d_Theta, "null pointer");
+    OMB_CHECK_ARG(r > 0 && s > 0 && s * r < (1ll << 30), "bad size");
+    int g = (int)ceil_div(s * r, 256);
+    if (g > 1024) g = 1024;
+    gather_rows_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(d_Ut, ld, (int)r, d_piv, (int)s, d_Theta, d_cnt, d_cnt_s);
+    return check_launch("gather_rows_kernel");
+}
+
+extern "C" int omb_modes_to_rows(const double* d_Ut, int64_t ld, int64_t n, int64_t r, double* d_Ur, void* stream)
+{
+    OMB_CHECK_ARG(d_Ut && d_Ur, "null pointer");
+    OMB_CHECK_ARG(n > 0 && r > 0 && ld >= n, "bad size");
+    int64_t g = ceil_div(n, 32) * ceil_div(r, 32);
+    if (g > (int64_t)sm_count() * 32) g = (int64_t)sm_count() * 32;
+    modes_to_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_Ut, ld, n, (int)r, d_Ur);
+    return check_launch("modes_to_rows_kernel");
+}
+
+extern "C" int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, int64_t ld, double* d_vn,
+                                 void* stream)
+{
+    OMB_CHECK_ARG(d_Ur && d_Ut, "null pointer");
+    OMB_CHECK_ARG(n > 0 && r > 0 && ld >= n, "bad size");
+    int64_t g = ceil_div(n, 32) * ceil_div(r, 32);
+    if (g > (int64_t)sm_count() * 32) g = (int64_t)sm_count() * 32;
+    rows_to_modes_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_Ur, n, (int)r, d_Ut, ld);
+    int rc = check_launch("rows_to_modes_kernel");
+    if (rc || !d_vn) return rc;
+    int64_t g2 = ceil_div(n, 256);
+    if (g2 > (int64_t)sm_count() * 8) g2 = (int64_t)sm_count() * 8;
+    row_norms_kernel<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_Ut, ld, n, (int)r, d_vn);
+    return check_launch("row_norms_kernel");
+}
+
+extern "C" int omb_ols_predict(const double* d_Y, const double* d_cnt_s, const double* d_scl_s,
+                               const double* d_PinvT, int64_t N, int64_t s, int64_t r, double* d_A, void* stream)
+{
+    OMB_CHECK_ARG(d_Y && d_PinvT && d_A, "null pointer");
+    OMB_CHECK_ARG(N > 0 && s > 0 && r > 0 && s < (1 << 24), "bad size");
+    int64_t tiles = ceil_div(N, OT) * ceil_div(r, OT);
+    if (tiles > (int64_t)sm_count() * 8) tiles = (int64_t)sm_count() * 8;
+    ols_gemm_kernel<0><<<(unsigned)tiles, O_THREADS, 0, (cudaStream_t)stream>>>(d_Y, d_PinvT, N, r, (int)s, s, d_cnt_s,
+                                                                                 d_scl_s, 1, 0, d_A);
+    return check_launch("ols_gemm_kernel<predict>");
+}
+
+extern "C" int omb_reconstruct(const double* d_Ut, int64_t ld, int64_t r, const double* d_A, int64_t N,
+                               const double* d_cnt, const double* d_scl, int64_t n_c, int64_t row0, int64_t nrows,
+                               double* d_out, void* stream)
+{
+    OMB_CHECK_ARG(d_Ut && d_A && d_out, "null pointer");
+    OMB_CHECK_ARG(N > 0 && r > 0 && nrows > 0 && row0 >= 0 && n_c > 0 && r < (1 << 24), "bad size");
+    OMB_CHECK_ARG(row0 + nrows <= ld, "row range exceeds ld");
+    int64_t tiles = ceil_div(nrows, OT) * ceil_div(N, OT);
+    if (tiles > (int64_t)sm_count() * 8) tiles = (int64_t)sm_count() * 8;
+    ols_gemm_kernel<1><<<(unsigned)tiles, O_THREADS, 0, (cudaStream_t)stream>>>(d_Ut, d_A, nrows, N, (int)r, ld, d_cnt,
+                                                                                 d_scl, n_c, row0, d_out);
+    return check_launch("ols_gemm_kernel<reconstruct>");
+}

@@ -1,0 +1,417 @@
+// stats.cu -- K1: centring/scaling statistics, bit-exact with numpy's pairwise add.reduce.
+//
+// Replaces np.average(x, axis=1), np.std(x), np.max(x), np.min(x) over the n_cells-row feature
+// blocks (reference sparse_sensing.py:110-161).  numpy reduces a contiguous FP64 range with a
+// fixed tree: ranges > 128 elements split at n2 = (n/2) & ~7, leaves (<= 128 elements) are summed
+// with 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail.
+// The kernels evaluate exactly that tree: one 8-lane group owns one leaf (lane k = accumulator k,
+// a 64-byte coalesced read per step), leaves are combined up the tree in shared memory and then in
+// a small global up-sweep.  Nodes that do not exist at a given depth are tracked with a flag, not
+// with +0.0, so even the sign of zero follows numpy.
+#include "common.cuh"
+#include "../../include/omb200.h"
+
+namespace omb {
+
+// ---------------------------------------------------------------------------------------------
+// leaf and subtree evaluation
+// ---------------------------------------------------------------------------------------------
+struct MapId {
+    __device__ __forceinline__ double operator()(double x) const { return x; }
+};
+struct MapSqDev {
+    double mu;
+    __device__ __forceinline__ double operator()(double x) const
+    {
+        double d = x - mu;
+        return d * d;
+    }
+};
+
+// Sum of a leaf (n <= 128) by an 8-lane group; every lane of the group returns the result.
+// `gmask` is the shuffle mask of the group's 8 lanes.  Optionally tracks min/max of raw values.
+template <class Map, bool MINMAX>
+__device__ __forceinline__ double leaf_sum(const double* __restrict__ a, int64_t n, int l8, unsigned gmask,
+                                           Map f, double& lo, double& hi)
+{
+    if (n < 8) {
+        double res = -0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            double x = a[i];
+            if (MINMAX) { lo = fmin(lo, x); hi = fmax(hi, x); }
+            res += f(x);
+        }
+        return res;
+    }
+    double x = a[l8];
+    if (MINMAX) { lo = fmin(lo, x); hi = fmax(hi, x); }
+    double r = f(x);
+    const int64_t nfull = n - (n % 8);
+    for (int64_t i = 8; i < nfull; i += 8) {
+        x = a[i + l8];
+        if (MINMAX) { lo = fmin(lo, x); hi = fmax(hi, x); }
+        r += f(x);
+    }
+    r += __shfl_xor_sync(gmask, r, 1);
+    r += __shfl_xor_sync(gmask, r, 2);
+    r += __shfl_xor_sync(gmask, r, 4);
+    for (int64_t i = nfull; i < n; ++i) {
+        x = a[i];
+        if (MINMAX) { lo = fmin(lo, x); hi = fmax(hi, x); }
+        r += f(x);
+    }
+    return r;
+}
+
+// Full pairwise tree of a range by one 8-lane group (used for rows with m > 128).
+template <class Map>
+__device__ double tree_sum_group(const double* __restrict__ a, int64_t n, int l8, unsigned gmask, Map f)
+{
+    if (n <= 128) {
+        double lo = 0, hi = 0;
+        return leaf_sum<Map, false>(a, n, l8, gmask, f, lo, hi);
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    double left = tree_sum_group(a, n2, l8, gmask, f);
+    double right = tree_sum_group(a + n2, n - n2, l8, gmask, f);
+    return left + right;
+}
+
+// Walk `depth` levels down numpy's tree from (off, n) following the bits of `path` (MSB first).
+// Returns false when that slot does not exist (an ancestor is already a leaf and this is not its
+// left-most descendant).
+__device__ __forceinline__ bool descend(int64_t& off, int64_t& n, uint32_t path, int depth)
+{
+    for (int d = depth - 1; d >= 0; --d) {
+        if (n <= 128) return (path & ((2u << d) - 1u)) == 0u;
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        if ((path >> d) & 1u) { off += n2; n -= n2; }
+        else n = n2;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row means: one 8-lane group per row
+// ---------------------------------------------------------------------------------------------
+constexpr int RM_THREADS = 256;
+
+__global__ void __launch_bounds__(RM_THREADS)
+row_means_kernel(const double* __restrict__ X, int64_t rows, int64_t m, double* __restrict__ cnt)
+{
+    const int l8 = threadIdx.x & 7;
+    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+    const int64_t g0 = ((int64_t)blockIdx.x * RM_THREADS + threadIdx.x) >> 3;
+    const int64_t gstride = ((int64_t)gridDim.x * RM_THREADS) >> 3;
+    const double dm = (double)m;
+    for (int64_t row = g0; row < rows; row += gstride) {
+        double s = tree_sum_group(X + row * m, m, l8, gmask, MapId());
+        if (l8 == 0) cnt[row] = s / dm;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// block tree sum.  Tree depth D = LT + LC: a CTA evaluates one depth-LT node (a subtree of 2^LC
+// slots) and writes its value to the level-LT array; a second kernel sweeps the top LT levels.
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_THREADS = 256;
+constexpr int BS_LC_MAX = 6;                 // up to 64 leaves (~6.5K elements) per CTA subtree
+
+struct BlockPlan { int D, LT, LC; };
+
+static BlockPlan make_plan(int64_t n0)
+{
+    int D = 0;
+    // all leaves are at depth <= D once n0 / 2^D + 15 <= 128
+    while ((double)n0 / (double)(1ull << D) + 15.0 > 128.0) ++D;
+    BlockPlan p;
+    p.D = D;
+    p.LC = D < BS_LC_MAX ? D : BS_LC_MAX;
+    p.LT = D - p.LC;
+    return p;
+}
+
+template <int MODE>   // 0: sum/min/max   1: sum of squared deviations about stats[f*4]/count
+__global__ void __launch_bounds__(BS_THREADS)
+block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LT, int LC,
+                  const double* __restrict__ stats, double mean_count, double* __restrict__ top_val,
+                  unsigned char* __restrict__ top_flag, double* __restrict__ top_min,
+                  double* __restrict__ top_max)
+{
+    __shared__ double s_val[1 << BS_LC_MAX];
+    __shared__ unsigned char s_flag[1 << BS_LC_MAX];
+    __shared__ double s_lo[BS_THREADS / 32], s_hi[BS_THREADS / 32];
+
+    const int f = blockIdx.y;
+    const int64_t ntop = (int64_t)1 << LT;
+    const double* base = X + (int64_t)f * block_elems;
+    const int l8 = threadIdx.x & 7;
+    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+    const int grp = threadIdx.x >> 3;
+    constexpr int NGRP = BS_THREADS / 8;
+    const int nslots = 1 << LC;
+    double mu = 0.0;
+    if (MODE == 1) mu = stats[f * 4 + 0] / mean_count;
+
+    for (int64_t node = blockIdx.x; node < ntop; node += gridDim.x) {
+        int64_t off = 0, n = block_elems;
+        const bool present = descend(off, n, (uint32_t)node, LT);
+        double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
+        if (present) {
+            for (int slot = grp; slot < nslots; slot += NGRP) {
+                int64_t o2 = off, n2 = n;
+                bool here = descend(o2, n2, (uint32_t)slot, LC);
+                double v = 0.0;
+                if (here) {
+                    if (MODE == 0) v = leaf_sum<MapId, true>(base + o2, n2, l8, gmask, MapId(), lo, hi);
+                    else { MapSqDev mp; mp.mu = mu; v = leaf_sum<MapSqDev, false>(base + o2, n2, l8, gmask, mp, lo, hi); }
+                }
+                if (l8 == 0) { s_val[slot] = v; s_flag[slot] = here ? 1 : 0; }
+            }
+        }
+        __syncthreads();
+        if (present) {
+            // up-sweep: a node's value ends in its left-most descendant slot
+            for (int half = 1; half < nslots; half <<= 1) {
+                int idx = threadIdx.x * 2 * half;
+                if (idx + half < nslots && s_flag[idx + half]) s_val[idx] = s_val[idx] + s_val[idx + half];
+                __syncthreads();
+            }
+        }
+        if (MODE == 0) {
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+                hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+            }
+            if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            top_val[(int64_t)f * ntop + node] = present ? s_val[0] : 0.0;
+            top_flag[(int64_t)f * ntop + node] = present ? 1 : 0;
+            if (MODE == 0) {
+                for (int w = 1; w < BS_THREADS / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+                top_min[(int64_t)f * ntop + node] = lo;
+                top_max[(int64_t)f * ntop + node] = hi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA per feature: sweep the top LT levels in place, reduce min/max, write stats.
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+block_top_kernel(int LT, double* __restrict__ top_val, const unsigned char* __restrict__ top_flag,
+                 const double* __restrict__ top_min, const double* __restrict__ top_max,
+                 double* __restrict__ stats)
+{
+    const int f = blockIdx.x;
+    const int64_t ntop = (int64_t)1 << LT;
+    double* val = top_val + (int64_t)f * ntop;
+    const unsigned char* flag = top_flag + (int64_t)f * ntop;
+    for (int64_t half = 1; half < ntop; half <<= 1) {
+        for (int64_t t = threadIdx.x; t * 2 * half + half < ntop; t += blockDim.x) {
+            int64_t idx = t * 2 * half;
+            if (flag[idx + half]) val[idx] = val[idx] + val[idx + half];
+        }
+        __syncthreads();
+    }
+    if (MODE == 0) {
+        __shared__ double s_lo[32], s_hi[32];
+        double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
+        for (int64_t t = threadIdx.x; t < ntop; t += blockDim.x) {
+            lo = fmin(lo, top_min[(int64_t)f * ntop + t]);
+            hi = fmax(hi, top_max[(int64_t)f * ntop + t]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+            stats[f * 4 + 0] = val[0];
+            stats[f * 4 + 1] = lo;
+            stats[f * 4 + 2] = hi;
+        }
+    } else {
+        if (threadIdx.x == 0) stats[f * 4 + 3] = val[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale factors from block statistics (one thread per feature), optional scalar centring
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_scale_kernel(const double* __restrict__ stats, int F, double count, int scale_type,
+                                      double* __restrict__ scl)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double sum = stats[f * 4 + 0], lo = stats[f * 4 + 1], hi = stats[f * 4 + 2], q = stats[f * 4 + 3];
+    const double mean = sum / count;
+    const double var = q / count;
+    const double sd = sqrt(var);
+    double s = 1.0;
+    switch (scale_type) {
+        case OMB_SCALE_STD: s = sd; break;
+        case OMB_SCALE_NONE: s = 1.0; break;
+        case OMB_SCALE_PARETO: s = sqrt(sd); break;
+        case OMB_SCALE_VAST: s = (sd * sd) / mean; break;
+        case OMB_SCALE_RANGE: s = hi - lo; break;
+        case OMB_SCALE_LEVEL: s = mean; break;
+        case OMB_SCALE_MAX: s = hi; break;
+        case OMB_SCALE_VARIANCE: s = var; break;
+        case OMB_SCALE_POISSON: s = sqrt(mean); break;
+        case OMB_SCALE_L2NORM: s = sqrt(fma(count * mean, mean, q)); break;  // sum x^2 = q + N mean^2
+        default: break;
+    }
+    scl[f] = s;
+}
+
+__global__ void fill_cnt_kernel(const double* __restrict__ stats, double count, int64_t n_c_loc,
+                                double* __restrict__ cnt)
+{
+    const int f = blockIdx.y;
+    const double mean = stats[f * 4 + 0] / count;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_c_loc;
+         i += (int64_t)gridDim.x * blockDim.x)
+        cnt[(int64_t)f * n_c_loc + i] = mean;
+}
+
+// X0 = (X - cnt) / scl  (IEEE subtraction and division, same bits as numpy broadcasting)
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const double* __restrict__ X, int64_t n_c, int64_t m, const double* __restrict__ cnt,
+                  const double* __restrict__ scl, double* __restrict__ X0)
+{
+    const int f = blockIdx.y;
+    const double s = scl ? scl[f] : 1.0;
+    const int64_t total = n_c * m;
+    const double* xb = X + (int64_t)f * total;
+    double* ob = X0 + (int64_t)f * total;
+    const double* cb = cnt ? cnt + (int64_t)f * n_c : nullptr;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / m;
+        const double c = cb ? cb[row] : 0.0;
+        ob[e] = (xb[e] - c) / s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unscale_kernel(const double* __restrict__ x0, const double* __restrict__ cnt, const double* __restrict__ scl,
+               int64_t n_c, int64_t n, double* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x0[i];
+        if (scl) v = scl[i / n_c] * v;
+        if (cnt) v = v + cnt[i];
+        out[i] = v;
+    }
+}
+
+}  // namespace omb
+
+using namespace omb;
+
+extern "C" int omb_unscale(const double* d_x0, const double* d_cnt, const double* d_scl, int64_t n_c, int64_t n,
+                           double* d_out, void* stream)
+{
+    OMB_CHECK_ARG(d_x0 && d_out, "null pointer");
+    OMB_CHECK_ARG(n > 0 && n_c > 0, "non-positive size");
+    int64_t g = ceil_div(n, 256);
+    if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
+    unscale_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_x0, d_cnt, d_scl, n_c, n, d_out);
+    return check_launch("unscale_kernel");
+}
+
+extern "C" int omb_row_means(const double* d_X, int64_t rows, int64_t m, double* d_cnt, void* stream)
+{
+    OMB_CHECK_ARG(d_X && d_cnt, "null pointer");
+    OMB_CHECK_ARG(rows > 0 && m > 0, "non-positive size");
+    int64_t groups_per_cta = RM_THREADS / 8;
+    int64_t grid = ceil_div(rows, groups_per_cta);
+    int64_t cap = (int64_t)sm_count() * 32;
+    if (grid > cap) grid = cap;
+    row_means_kernel<<<(unsigned)grid, RM_THREADS, 0, (cudaStream_t)stream>>>(d_X, rows, m, d_cnt);
+    return check_launch("row_means_kernel");
+}
+
+extern "C" int64_t omb_block_stats_ws_bytes(int64_t F, int64_t block_elems)
+{
+    if (F <= 0 || block_elems <= 0) return 0;
+    BlockPlan p = make_plan(block_elems);
+    int64_t ntop = (int64_t)1 << p.LT;
+    // val + min + max (doubles) + flags, per feature
+    return F * ntop * (3 * (int64_t)sizeof(double)) + round_up(F * ntop, 256) + 256;
+}
+
+extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems, int mode,
+                               int64_t mean_count, double* d_out, void* d_ws, void* stream)
+{
+    OMB_CHECK_ARG(d_X && d_out && d_ws, "null pointer");
+    OMB_CHECK_ARG(F > 0 && block_elems > 0, "non-positive size");
+    OMB_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+    BlockPlan p = make_plan(block_elems);
+    OMB_CHECK_ARG(p.LT <= 30, "block too large");
+    const int64_t ntop = (int64_t)1 << p.LT;
+    double* top_val = (double*)d_ws;
+    double* top_min = top_val + F * ntop;
+    double* top_max = top_min + F * ntop;
+    unsigned char* top_flag = (unsigned char*)(top_max + F * ntop);
+    int64_t gx = ntop;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, (unsigned)F);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0)
+        block_tree_kernel<0><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LT, p.LC, d_out, (double)mean_count, top_val,
+                                                           top_flag, top_min, top_max);
+    else
+        block_tree_kernel<1><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LT, p.LC, d_out, (double)mean_count, top_val,
+                                                           top_flag, top_min, top_max);
+    int rc = check_launch("block_tree_kernel");
+    if (rc) return rc;
+    if (mode == 0)
+        block_top_kernel<0><<<(unsigned)F, 1024, 0, st>>>(p.LT, top_val, top_flag, top_min, top_max, d_out);
+    else
+        block_top_kernel<1><<<(unsigned)F, 1024, 0, st>>>(p.LT, top_val, top_flag, top_min, top_max, d_out);
+    return check_launch("block_top_kernel");
+}
+
+extern "C" int omb_finalize_scale(const double* d_stats, int64_t F, int64_t count, int scale_type,
+                                  double* d_scl, int fill_cnt, double* d_cnt, int64_t n_c_loc, void* stream)
+{
+    OMB_CHECK_ARG(d_stats && d_scl, "null pointer");
+    OMB_CHECK_ARG(F > 0 && count > 0, "non-positive size");
+    OMB_CHECK_ARG(scale_type >= 0 && scale_type <= OMB_SCALE_L2NORM, "unknown scale_type");
+    cudaStream_t st = (cudaStream_t)stream;
+    finalize_scale_kernel<<<(unsigned)ceil_div(F, 64), 64, 0, st>>>(d_stats, (int)F, (double)count, scale_type, d_scl);
+    int rc = check_launch("finalize_scale_kernel");
+    if (rc) return rc;
+    if (fill_cnt) {
+        OMB_CHECK_ARG(d_cnt && n_c_loc > 0, "fill_cnt needs d_cnt and n_c_loc");
+        int64_t gx = ceil_div(n_c_loc, 256);
+        if (gx > 4096) gx = 4096;
+        dim3 grid((unsigned)gx, (unsigned)F);
+        fill_cnt_kernel<<<grid, 256, 0, st>>>(d_stats, (double)count, n_c_loc, d_cnt);
+        rc = check_launch("fill_cnt_kernel");
+    }
+    return rc;
+}
+
+extern "C" int omb_scale_rows(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
+                              const double* d_scl, double* d_X0, void* stream)
+{
+    OMB_CHECK_ARG(d_X && d_X0, "null pointer");
+    OMB_CHECK_ARG(F > 0 && n_c > 0 && m > 0, "non-positive size");
+    int64_t gx = ceil_div(n_c * m, 256);
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, (unsigned)F);
+    scale_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, n_c, m, d_cnt, d_scl, d_X0);
+    return check_launch("scale_rows_kernel");
+}

@@ -1,0 +1,266 @@
+"""Device engine: owns the HBM-resident state of one ROM/SPR object and drives libomb200.so.
+
+PyTorch is plumbing only (device allocations, the current CUDA stream, the m x m eigensolve /
+s x r pseudo-inverse on device, torch.distributed for the tiny cross-rank exchanges); every pass
+over the n-row data is a hand-written sm_100a kernel called through the C ABI (include/omb200.h).
+
+Data layout in HBM (FP64 throughout):
+    X      (F * n_c_loc, m) C-order snapshot shard, feature-major, exactly the reference's layout
+    cnt    (F * n_c_loc,)   centring value per row          (reference X_cnt[:, 0])
+    scl    (F,)             scale per feature block         (reference X_scl[f * n_points, 0])
+    Ut     (r, ld)          mode-major basis, Ut[q, i] = U_r[i, q]; ld = n_loc rounded up to 16
+    work   (r, ld)          trailing matrix of the pivoted QR
+With torch.distributed initialised, every rank holds the cells [c0, c0 + n_c_loc) of EVERY
+feature; only F*4 statistics, the m x m Gram and (per pivot step) one small record cross NVLink.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SCALE_CODES = {"std": 0, "none": 1, "pareto": 2, "vast": 3, "range": 4, "level": 5, "max": 6,
+               "variance": 7, "poisson": 8, "l2-norm": 9}
+NEEDS_SQDEV = {"std", "pareto", "vast", "variance", "l2-norm"}
+EPS = float(np.finfo(np.float64).eps) / 2  # unit roundoff 2^-53
+
+
+def require_cuda():
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.OmbError("openmeasure_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def ld_for(n):
+    return (int(n) + 15) // 16 * 16
+
+
+class Engine:
+    def __init__(self, X_dev, n_features, group=None):
+        require_cuda()
+        assert X_dev.is_cuda and X_dev.dtype == torch.float64 and X_dev.dim() == 2
+        if not X_dev.is_contiguous():
+            X_dev = X_dev.contiguous()
+        self.X = X_dev
+        self.dev = X_dev.device
+        self.F = int(n_features)
+        self.n_loc, self.m = (int(v) for v in X_dev.shape)
+        assert self.n_loc % self.F == 0
+        self.n_c_loc = self.n_loc // self.F
+        self.group = group
+        self.world = 1
+        self.rank = 0
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                 and group is not False):
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                self.world = dist.get_world_size(group)
+                self.rank = dist.get_rank(group)
+        if self.world > 1:
+            import torch.distributed as dist
+            counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+            counts[self.rank] = self.n_c_loc
+            dist.all_reduce(counts, group=self.group)
+            self.cells_per_rank = [int(c) for c in counts.cpu()]
+        else:
+            self.cells_per_rank = [self.n_c_loc]
+        self.n_c = sum(self.cells_per_rank)             # global cells per feature
+        self.cell0 = sum(self.cells_per_rank[: self.rank])
+        self.cnt = None
+        self.scl = None
+        self.Ut = None
+        self.vn = None
+        self.r = None
+        self.ld = ld_for(self.n_loc)
+        self.timings = {}
+
+    # ------------------------------------------------------------------------------------ K1
+    def stats(self, scale_type="std", axis_cnt=1):
+        """Centring vector and per-feature scale (sparse_sensing.py:106-167)."""
+        if scale_type not in SCALE_CODES:
+            raise NotImplementedError("The scaling method selected has not been implemented yet")
+        F, ncl, m = self.F, self.n_c_loc, self.m
+        st = _stream()
+        cnt = torch.empty(self.n_loc, dtype=torch.float64, device=self.dev)
+        stats = torch.zeros(F * 4, dtype=torch.float64, device=self.dev)
+        blk = ncl * m
+        ws = _ws(_lib.load().omb_block_stats_ws_bytes(F, blk), self.dev)
+        if axis_cnt == 1:
+            _lib.call("omb_row_means", _p(self.X), self.n_loc, m, _p(cnt), st)
+        count = self.n_c * m
+        _lib.call("omb_block_stats", _p(self.X), F, blk, 0, count, _p(stats), _p(ws), st)
+        if self.world > 1:
+            stats = self._combine_stats(stats, sq=False)
+        if scale_type in NEEDS_SQDEV:
+            _lib.call("omb_block_stats", _p(self.X), F, blk, 1, count, _p(stats), _p(ws), st)
+            if self.world > 1:
+                stats = self._combine_stats(stats, sq=True)
+        scl = torch.empty(F, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_finalize_scale", _p(stats), F, count, SCALE_CODES[scale_type], _p(scl),
+                  1 if axis_cnt is None else 0, _p(cnt), ncl, st)
+        self.cnt, self.scl, self.block_stats = cnt, scl, stats
+        return cnt, scl
+
+    def _combine_stats(self, stats, sq):
+        """Fixed-order (rank 0..G-1) combination of the per-rank block statistics."""
+        import torch.distributed as dist
+        allst = torch.empty(self.world * stats.numel(), dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(allst, stats, group=self.group)
+        allst = allst.view(self.world, self.F, 4)
+        out = stats.view(self.F, 4).clone()
+        if not sq:
+            acc = allst[0, :, 0].clone()
+            for g in range(1, self.world):
+                acc = acc + allst[g, :, 0]
+            out[:, 0] = acc
+            out[:, 1] = allst[:, :, 1].min(dim=0).values
+            out[:, 2] = allst[:, :, 2].max(dim=0).values
+        else:
+            acc = allst[0, :, 3].clone()
+            for g in range(1, self.world):
+                acc = acc + allst[g, :, 3]
+            out[:, 3] = acc
+        return out.reshape(-1).contiguous()
+
+    def set_scale_feature(self, f, value):
+        self.scl[f] = value
+
+    # ------------------------------------------------------------------------------------ K3
+    def gram(self, centred=True, scaled=True):
+        """G = X0^T X0 (m x m) from per-feature Grams of the centred rows."""
+        F, ncl, m = self.F, self.n_c_loc, self.m
+        st = _stream()
+        Gf = torch.empty(F * m * m, dtype=torch.float64, device=self.dev)
+        ws = _ws(_lib.load().omb_gram_ws_bytes(F, ncl, m), self.dev)
+        _lib.call("omb_gram", _p(self.X), F, ncl, m, _p(self.cnt if centred else None), _p(Gf), _p(ws), st)
+        G = torch.empty(m, m, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_gram_combine", _p(Gf), F, m, _p(self.scl if scaled else None), _p(G), st)
+        if self.world > 1:
+            import torch.distributed as dist
+            gathered = torch.empty(self.world, m, m, dtype=torch.float64, device=self.dev)
+            dist.all_gather_into_tensor(gathered, G, group=self.group)
+            G = gathered[0].clone()
+            for g in range(1, self.world):          # fixed order: identical bits on every rank
+                G = G + gathered[g]
+        return G
+
+    @staticmethod
+    def eig_pod(G):
+        """m x m eigensolve -> singular values (descending) and right singular vectors."""
+        w, V = torch.linalg.eigh(G)
+        w = torch.flip(w, dims=(0,))
+        V = torch.flip(V, dims=(1,)).contiguous()
+        S = torch.sqrt(torch.clamp(w, min=0.0))
+        # deterministic sign: the largest-magnitude component of each right vector is positive
+        idx = torch.argmax(V.abs(), dim=0)
+        sgn = torch.sign(V[idx, torch.arange(V.shape[1], device=V.device)])
+        sgn = torch.where(sgn == 0, torch.ones_like(sgn), sgn)
+        return S, V * sgn
+
+    # ------------------------------------------------------------------------------------ K5
+    def backproject(self, W, centred=True, scaled=True, norms=True):
+        """Ut (r x ld, mode-major) = (X0 W)^T, plus the initial pivoted-QR norms."""
+        W = W.contiguous()
+        m, r = (int(v) for v in W.shape)
+        assert m == self.m
+        Ut = torch.zeros(r, self.ld, dtype=torch.float64, device=self.dev)
+        vn = torch.zeros(self.ld, dtype=torch.float64, device=self.dev) if norms else None
+        _lib.call("omb_backproject", _p(self.X), self.F, self.n_c_loc, self.m,
+                  _p(self.cnt if centred else None), _p(self.scl if scaled else None), _p(W), r,
+                  _p(Ut), self.ld, _p(vn), _stream())
+        self.Ut, self.vn, self.r = Ut, vn, r
+        return Ut
+
+    def set_basis_rows(self, Ur_dev):
+        """Install a user-supplied basis (n_loc, r) (fit(basis=...), attribute assignment)."""
+        Ur_dev = Ur_dev.contiguous()
+        n, r = (int(v) for v in Ur_dev.shape)
+        assert n == self.n_loc
+        Ut = torch.zeros(r, self.ld, dtype=torch.float64, device=self.dev)
+        vn = torch.zeros(self.ld, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_rows_to_modes", _p(Ur_dev), n, r, _p(Ut), self.ld, _p(vn), _stream())
+        self.Ut, self.vn, self.r = Ut, vn, r
+
+    def basis_rows(self):
+        """(n_loc, r) C-order copy of the basis on device."""
+        out = torch.empty(self.n_loc, self.r, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_modes_to_rows", _p(self.Ut), self.ld, self.n_loc, self.r, _p(out), _stream())
+        return out
+
+    def mask_rows(self, mask_dev):
+        """optimal_placement(mask=...): zero the excluded rows of the basis in place (:737-738)."""
+        keep = torch.zeros(self.ld, dtype=torch.bool, device=self.dev)
+        keep[: self.n_loc] = mask_dev
+        self.Ut[:, : self.n_loc].mul_(keep[: self.n_loc].to(torch.float64))
+        self.vn = None      # recomputed by the placement
+
+    # ------------------------------------------------------------------------------------ K6
+    def qrcp(self, s=None, block=8):
+        """Pivoted QR over the candidate rows; returns (piv, rdiag, gap) as device tensors."""
+        if self.world > 1:
+            raise NotImplementedError("multi-rank placement is driven by openmeasure_b200.parallel")
+        r = self.r
+        s = r if s is None else int(s)
+        work = torch.empty(r, self.ld, dtype=torch.float64, device=self.dev)
+        ws = _ws(_lib.load().omb_qrcp_ws_bytes(self.n_loc, r), self.dev)
+        piv = torch.empty(s, dtype=torch.int64, device=self.dev)
+        rdiag = torch.empty(s, dtype=torch.float64, device=self.dev)
+        gap = torch.empty(s, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_qrcp", _p(self.Ut), self.ld, self.n_loc, r, s, _p(self.vn), _p(work), _p(ws),
+                  int(block), 0, _p(piv), _p(rdiag), _p(gap), _stream())
+        return piv, rdiag, gap
+
+    # ------------------------------------------------------------------------------- K8 - K11
+    def gather(self, piv_dev):
+        s = int(piv_dev.numel())
+        Theta = torch.empty(s, self.r, dtype=torch.float64, device=self.dev)
+        cnt_s = torch.empty(s, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_gather_rows", _p(self.Ut), self.ld, self.r, _p(piv_dev), s, _p(Theta),
+                  _p(self.cnt), _p(cnt_s), _stream())
+        return Theta, cnt_s
+
+    def ols_predict(self, Y_dev, cnt_s, scl_s, PinvT):
+        N, s = (int(v) for v in Y_dev.shape)
+        r = int(PinvT.shape[1])
+        A = torch.empty(N, r, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_ols_predict", _p(Y_dev.contiguous()), _p(cnt_s), _p(scl_s), _p(PinvT.contiguous()),
+                  N, s, r, _p(A), _stream())
+        return A
+
+    def reconstruct(self, A_dev, row0=0, nrows=None, out=None):
+        """rows [row0, row0+nrows) of scl * (U_r A^T) + cnt, as a (nrows, N) device tensor."""
+        A_dev = A_dev.contiguous()
+        N, r = (int(v) for v in A_dev.shape)
+        assert r == self.r
+        nrows = self.n_loc - row0 if nrows is None else int(nrows)
+        if out is None:
+            out = torch.empty(nrows, N, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_reconstruct", _p(self.Ut), self.ld, r, _p(A_dev), N, _p(self.cnt), _p(self.scl),
+                  self.n_c_loc, int(row0), nrows, _p(out), _stream())
+        return out
+
+    def scaled_matrix(self):
+        """X0 = (X - cnt)/scl materialised on device (only when user code asks for .X0)."""
+        X0 = torch.empty_like(self.X)
+        _lib.call("omb_scale_rows", _p(self.X), self.F, self.n_c_loc, self.m, _p(self.cnt), _p(self.scl),
+                  _p(X0), _stream())
+        return X0
+
+    def unscale(self, x0_dev):
+        out = torch.empty_like(x0_dev)
+        _lib.call("omb_unscale", _p(x0_dev.contiguous()), _p(self.cnt), _p(self.scl), self.n_c_loc,
+                  int(x0_dev.numel()), _p(out), _stream())
+        return out

@@ -1,0 +1,468 @@
+"""B200-native mirror of OpenMEASURE's snapshot-POD sparse-sensing classes.
+
+Drop-in for the hot path of /root/reference/src/openmeasure/sparse_sensing.py:
+
+    ROM/SPR(X, n_features, xyz) -> fit(...) -> optimal_placement() -> train(C) -> predict(y)
+    -> reconstruct(ap)
+
+Same class and method names, argument meaning, attributes and exception types as the reference
+(ROM: sparse_sensing.py:18-511, SPR: :513-901); the numerics run on the GPU through the C ABI of
+libomb200.so (see engine.py).  There is no CPU fallback: without the CUDA library and a CUDA
+device every compute call raises.
+
+Deliberate differences (DESIGN.md "Reference quirks"):
+  * optimal_placement() returns a lazy one-hot `SensorMatrix` (shape, C[i, :], C @ x, C.dot,
+    np.asarray(C) all work) instead of a dense s x n float array (13 GB at config 3);
+  * X0 and Ur are materialised on the host only when read;
+  * POD modes are defined up to sign (as in any SVD); singular values/reconstructions agree with
+    the reference to 1e-10, pivots are identical on non-degenerate inputs.
+Out of scope (raise NotImplementedError): GEM placement, constrained OLS ('COLS'), CPOD,
+adaptive_sampling, scale_limits -- see SURVEY.md section 8.
+"""
+import numpy as np
+import torch
+
+from . import engine as _eng
+
+_BROKEN_SCALES = ("vast_2", "vast_3", "vast_4")   # broadcast-fail in the reference (:147-157)
+
+
+class SensorMatrix:
+    """One-hot measurement matrix C (s x n): row j has a single 1 at column pivots[j].
+
+    Stands in for the dense array built at sparse_sensing.py:740-743.  Supports the idioms the
+    reference's README and tests use: C.shape, C[i, :], np.argmax(C[i, :]), C @ x, C.dot(x),
+    np.asarray(C)."""
+
+    def __init__(self, pivots, n):
+        self.pivots = np.asarray(pivots, dtype=np.int64)
+        self.shape = (int(self.pivots.size), int(n))
+        self.ndim = 2
+        self.dtype = np.dtype(np.float64)
+
+    def toarray(self):
+        C = np.zeros(self.shape)
+        C[np.arange(self.shape[0]), self.pivots] = 1
+        return C
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.toarray()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2:
+            rows, cols = key
+        else:
+            rows, cols = key, slice(None)
+        ridx = np.arange(self.shape[0])[rows]
+        if np.ndim(ridx) == 0:
+            row = np.zeros(self.shape[1])
+            row[self.pivots[ridx]] = 1
+            return row[cols]
+        sub = np.zeros((len(ridx), self.shape[1]))
+        sub[np.arange(len(ridx)), self.pivots[ridx]] = 1
+        return sub[:, cols]
+
+    def dot(self, x):
+        x = np.asarray(x)
+        if x.shape[0] != self.shape[1]:
+            raise ValueError("shapes not aligned")
+        return x[self.pivots]
+
+    __matmul__ = dot
+
+
+def _as_pivots(C):
+    """pivots of a one-hot C (SensorMatrix or dense), else None."""
+    if isinstance(C, SensorMatrix):
+        return C.pivots
+    if isinstance(C, np.ndarray) and C.ndim == 2:
+        piv = np.argmax(C, axis=1)
+        ok = (C[np.arange(C.shape[0]), piv] == 1).all() and (np.count_nonzero(C, axis=1) == 1).all()
+        return piv.astype(np.int64) if ok else None
+    return None
+
+
+class ROM:
+    """Reduced-order-model utilities: centring/scaling, POD, truncation, reconstruction
+    (reference ROM, sparse_sensing.py:18-511)."""
+
+    def __init__(self, X, n_features, xyz):
+        if type(X) is not np.ndarray:                     # :69-70
+            raise TypeError('The matrix X is not a numpy array.')
+        if type(n_features) is not int:                   # :71-72
+            raise TypeError('The parameter n_features is not an integer.')
+        self.X = X
+        self.n_features = n_features
+        self.xyz = xyz
+        n = X.shape[0]
+        self.n_points = n // n_features
+        if n % n_features != 0:                           # :80-81
+            raise Exception('The number of rows of X is not a multiple of n_features')
+        self._eng = None
+        self._host = {}
+
+    # ------------------------------------------------------------------ device plumbing
+    @classmethod
+    def from_device(cls, X_dev, n_features, xyz=None, group=None):
+        """Extension: build on an HBM-resident shard (torch CUDA float64 (F*n_c_loc, m)); with
+        torch.distributed initialised each rank passes its own cells of every feature."""
+        self = cls.__new__(cls)
+        if type(n_features) is not int:
+            raise TypeError('The parameter n_features is not an integer.')
+        if X_dev.shape[0] % n_features != 0:
+            raise Exception('The number of rows of X is not a multiple of n_features')
+        self.X = None
+        self.n_features = n_features
+        self.xyz = xyz
+        self._eng = _eng.Engine(X_dev, n_features, group=group)
+        self.n_points = self._eng.n_c_loc
+        self._host = {}
+        return self
+
+    def _engine(self):
+        if self._eng is None:
+            _eng.require_cuda()
+            X = self.X
+            if X.dtype != np.float64 or not X.flags.c_contiguous:
+                X = np.ascontiguousarray(X, dtype=np.float64)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            Xd = torch.empty(X.shape, dtype=torch.float64, device=dev)
+            Xd.copy_(torch.from_numpy(X), non_blocking=True)
+            self._eng = _eng.Engine(Xd, self.n_features, group=False)
+        return self._eng
+
+    def _n_rows(self):
+        return self.X.shape[0] if self.X is not None else self._eng.n_loc
+
+    # ------------------------------------------------------------------ lazy host mirrors
+    @property
+    def X_cnt(self):
+        if "X_cnt" not in self._host:
+            self._host["X_cnt"] = self._eng.cnt.cpu().numpy()[:, np.newaxis]
+        return self._host["X_cnt"]
+
+    @X_cnt.setter
+    def X_cnt(self, v):
+        self._host["X_cnt"] = v
+
+    @property
+    def X_scl(self):
+        if "X_scl" not in self._host:
+            scl = self._eng.scl.cpu().numpy()
+            self._host["X_scl"] = np.repeat(scl, self._eng.n_c_loc)[:, np.newaxis]
+        return self._host["X_scl"]
+
+    @X_scl.setter
+    def X_scl(self, v):
+        self._host["X_scl"] = v
+
+    @property
+    def X0(self):
+        if "X0" not in self._host:
+            self._host["X0"] = self._eng.scaled_matrix().cpu().numpy()
+        return self._host["X0"]
+
+    @X0.setter
+    def X0(self, v):
+        self._host["X0"] = v
+
+    @property
+    def Ur(self):
+        if "Ur" not in self._host:
+            self._host["Ur"] = self._eng.basis_rows().cpu().numpy()
+        return self._host["Ur"]
+
+    @Ur.setter
+    def Ur(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        eng = self._engine()
+        eng.set_basis_rows(torch.from_numpy(v).to(eng.dev))
+        self._host["Ur"] = v
+
+    # ------------------------------------------------------------------ scaling (a2, a12)
+    def scale_data(self, scale_type='std', axis_cnt=1):
+        """Centre and scale the snapshot matrix; returns X0 (sparse_sensing.py:83-171)."""
+        self._scale_stats(scale_type, axis_cnt)
+        return self.X0
+
+    def _scale_stats(self, scale_type, axis_cnt):
+        if scale_type in _BROKEN_SCALES or axis_cnt not in (1, None):
+            raise ValueError('could not broadcast the centring/scaling coefficient '
+                             '(same failure as the reference for this option)')
+        eng = self._engine()
+        if scale_type == 'median':
+            eng.stats('none', axis_cnt)
+            blocks = eng.X.view(eng.F, -1)
+            k = blocks.shape[1]
+            lo = torch.kthvalue(blocks, (k + 1) // 2, dim=1).values
+            hi = torch.kthvalue(blocks, k // 2 + 1, dim=1).values
+            eng.scl = ((lo + hi) / 2).contiguous()       # np.median (:140)
+        else:
+            eng.stats(scale_type, axis_cnt)
+        for k in ("X_cnt", "X_scl", "X0"):
+            self._host.pop(k, None)
+
+    def unscale_data(self, x0, sampling=None):
+        """x = X_scl * x0 + X_cnt (sparse_sensing.py:212-240)."""
+        eng = self._engine()
+        if sampling is not None:
+            raise NotImplementedError('sampling matrices are a "next" row (SURVEY.md 8f)')
+        xd = torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float64)).to(eng.dev)
+        return eng.unscale(xd).cpu().numpy()
+
+    # ------------------------------------------------------------------ POD (a3, a4)
+    def _choose_rank(self, exp_variance, m, select_modes, n_modes):
+        if select_modes == 'variance':                    # :314-324
+            if not 0 <= n_modes <= 100:
+                raise ValueError('The parameter n_modes is outside the[0-100] range.')
+            if n_modes == 100:
+                return m
+            r = 1
+            while exp_variance[r - 1] < n_modes:
+                r += 1
+            return r
+        if select_modes == 'number':                      # :326-331
+            if not type(n_modes) is int:
+                raise TypeError('The parameter n_modes is not an integer.')
+            if not 1 <= n_modes <= m:
+                raise ValueError('The parameter n_modes is outside the [1-m] range.')
+            return n_modes
+        raise ValueError('The select_mode value is wrong.')
+
+    def _validate_modes(self, select_modes, n_modes):
+        """Raise the reference's argument errors before any device work."""
+        if select_modes == 'variance':
+            if not 0 <= n_modes <= 100:
+                raise ValueError('The parameter n_modes is outside the[0-100] range.')
+        elif select_modes == 'number':
+            if not type(n_modes) is int:
+                raise TypeError('The parameter n_modes is not an integer.')
+            if not 1 <= n_modes <= self._m():
+                raise ValueError('The parameter n_modes is outside the [1-m] range.')
+        else:
+            raise ValueError('The select_mode value is wrong.')
+
+    def _m(self):
+        return self.X.shape[1] if self.X is not None else self._eng.m
+
+    def _pod(self, eng, select_modes, n_modes, centred, scaled):
+        G = eng.gram(centred=centred, scaled=scaled)
+        S, V = eng.eig_pod(G)
+        S_h = S.cpu().numpy()
+        lam = S_h ** 2
+        exp_variance = 100 * np.cumsum(lam) / np.sum(lam)     # :274-275
+        r = self._choose_rank(exp_variance, eng.m, select_modes, n_modes)
+        Sr = S[:r]
+        # modes whose singular value is numerically zero carry no information (row-centred data
+        # has rank m-1): back-project them with a zero weight instead of dividing by ~0
+        safe = Sr > S[0] * (eng.m * _eng.EPS)
+        W = torch.where(safe, 1.0 / torch.where(safe, Sr, torch.ones_like(Sr)), torch.zeros_like(Sr))
+        eng.backproject((V[:, :r] * W).contiguous(), centred=centred, scaled=scaled)
+        Ar = (V[:, :r] * Sr).cpu().numpy()                    # A = V Sigma (:273)
+        self.r = r
+        self._host.pop("Ur", None)
+        self.pod_sigma = S_h
+        self.pod_rel_err_bound = float(_eng.EPS * (S_h[0] / max(S_h[r - 1], 1e-300)) ** 2)
+        return Ar, exp_variance[:r]
+
+    def decomposition(self, X0, select_modes='variance', n_modes=99):
+        """POD of a scaled matrix X0 (n, m): returns (Ur, Ar, exp_variance[:r])
+        (sparse_sensing.py:242-279)."""
+        _eng.require_cuda()
+        self._validate_modes(select_modes, n_modes)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        X0d = torch.from_numpy(np.ascontiguousarray(X0, dtype=np.float64)).to(dev)
+        tmp = _eng.Engine(X0d, 1, group=False)
+        Ar, ev = self._pod(tmp, select_modes, n_modes, centred=False, scaled=False)
+        Ur = tmp.basis_rows().cpu().numpy()
+        return Ur, Ar, ev
+
+    def reduction(self, U, A, exp_variance, select_modes, n_modes):
+        """Truncate a basis to r modes (sparse_sensing.py:281-340)."""
+        r = self._choose_rank(exp_variance, A.shape[1], select_modes, n_modes)
+        if select_modes == 'number' and not 1 <= n_modes <= U.shape[1]:
+            raise ValueError('The parameter n_modes is outside the [1-m] range.')
+        self.r = r
+        return U[:, :r], A[:, :r]
+
+    # ------------------------------------------------------------------ fit (a5)
+    def fit(self, scale_type='std', axis_cnt=1, select_modes='variance', n_modes=99, basis=None):
+        """Scale, decompose (or take `basis=(Ur, Ar)`) and truncate (sparse_sensing.py:463-511)."""
+        if basis is None:
+            self._validate_modes(select_modes, n_modes)
+        self.scale_type = scale_type
+        self._scale_stats(scale_type, axis_cnt)
+        eng = self._engine()
+        if basis is None:
+            Ar, _ = self._pod(eng, select_modes, n_modes, centred=True, scaled=True)
+        else:
+            self.Ur = basis[0]
+            Ar = np.asarray(basis[1])
+        self.Ar = Ar
+        self.r = Ar.shape[1]
+        sig = np.linalg.norm(Ar, axis=0)                  # :504-507 (m x r, host-trivial)
+        self.Sigma_r = sig
+        self.Vr = Ar / sig
+
+    # ------------------------------------------------------------------ reconstruct (a11)
+    def reconstruct(self, Ar, sampling=None):
+        """X_rec (n, N) = unscale(Ur @ Ar.T) (sparse_sensing.py:342-375)."""
+        if sampling is not None:
+            raise NotImplementedError('sampling matrices are a "next" row (SURVEY.md 8f)')
+        Ar = np.asarray(Ar, dtype=np.float64)
+        if Ar.ndim < 2:
+            Ar = Ar[np.newaxis, :]
+        eng = self._engine()
+        Ad = torch.from_numpy(np.ascontiguousarray(Ar)).to(eng.dev)
+        return eng.reconstruct(Ad).cpu().numpy()
+
+    # ------------------------------------------------------------------ out of scope
+    def scale_limits(self, limits):
+        raise NotImplementedError('scale_limits (COLS only) is out of scope, SURVEY.md 8')
+
+    def adaptive_sampling(self, P, scale_type='std'):
+        raise NotImplementedError('adaptive_sampling is out of scope, SURVEY.md 8')
+
+    def CPOD(self, *args, **kwargs):
+        raise NotImplementedError('CPOD (cvxpy) is out of scope, SURVEY.md 8')
+
+
+class SPR(ROM):
+    """Sparse Placement for Reconstruction (reference SPR, sparse_sensing.py:513-901)."""
+
+    def __init__(self, X, n_features, xyz):
+        super().__init__(X, n_features, xyz)
+
+    # ------------------------------------------------------------------ placement (a7)
+    def optimal_placement(self, calc_type='qr', n_sensors=10, mask=None, d_min=0., verbose=False,
+                          block=8):
+        """QR-with-column-pivoting sensor placement (sparse_sensing.py:700-756, 'qr' branch).
+        `n_sensors`, `d_min`, `verbose` are ignored for 'qr' exactly as in the reference.
+        `block` (extension) = pivot steps between trailing-matrix rewrites."""
+        if calc_type == 'gem':
+            raise NotImplementedError('GEM placement is a "next" row (SURVEY.md 8f)')
+        if calc_type != 'qr':
+            raise NotImplementedError('The sensor selection method has not been implemented yet')
+        eng = self._engine()
+        if mask is not None:                              # :737-738, mutates the basis
+            eng.mask_rows(torch.from_numpy(np.asarray(mask, dtype=bool)).to(eng.dev))
+            self._host.pop("Ur", None)
+        piv, rdiag, gap = eng.qrcp(block=block)
+        self.qr_pivots = piv.cpu().numpy()
+        self.qr_rdiag = rdiag.cpu().numpy()
+        self.qr_gap = gap.cpu().numpy()
+        return SensorMatrix(self.qr_pivots, self._n_rows())
+
+    # ------------------------------------------------------------------ train (a8)
+    def train(self, C, is_Theta=False, limits=None, method='OLS', solver='CLARABEL', cond=False,
+              verbose=False):
+        """Theta = C . Ur (sparse_sensing.py:758-820)."""
+        n = self._n_rows()
+        if (C.shape[1] != n) and not is_Theta:
+            raise ValueError('The number of columns of C does not match the number'
+                             ' of rows of X.')
+        eng = self._engine()
+        if not is_Theta:
+            self.C = C
+            piv = _as_pivots(C)
+            if piv is not None:
+                Theta_d, cnt_s = eng.gather(torch.from_numpy(piv).to(eng.dev))
+            else:
+                Cd = self._dense_to_device(C, eng)
+                Ur_d = eng.basis_rows()
+                Theta_d = Cd @ Ur_d
+                cnt_s = Cd @ eng.cnt
+            self._cnt_s = cnt_s
+        else:
+            Theta_d = torch.from_numpy(np.ascontiguousarray(C, dtype=np.float64)).to(eng.dev)
+        if Theta_d.shape[1] != eng.r:
+            raise ValueError('The number of columns of Theta does not match the number'
+                             ' of columns of Ur.')
+        self._Theta_d = Theta_d
+        self._PinvT = torch.linalg.pinv(Theta_d, rtol=1e-15).T.contiguous()
+        self.Theta = Theta_d.cpu().numpy()
+        self.limits = limits
+        self.method = method
+        self.solver = solver
+        self.verbose = verbose
+        if cond == True:                                  # :813-820
+            Sth = torch.linalg.svdvals(Theta_d if Theta_d.shape[0] == Theta_d.shape[1]
+                                       else torch.linalg.pinv(Theta_d, rtol=1e-15))
+            self.k = float(Sth[0] / Sth[-1])
+
+    @staticmethod
+    def _dense_to_device(C, eng):
+        if hasattr(C, "toarray") and not isinstance(C, np.ndarray):
+            C = C.toarray()
+        return torch.from_numpy(np.ascontiguousarray(C, dtype=np.float64)).to(eng.dev)
+
+    # ------------------------------------------------------------------ predict (a9, a10)
+    def scale_vector(self, y):
+        """y0[:,0] = (y[:,0] - C X_cnt)/scl, y0[:,1] = y[:,1]/scl (sparse_sensing.py:553-584)."""
+        eng = self._engine()
+        y0 = np.zeros((y.shape[0], 2))
+        cnt_vector = self._cnt_s.cpu().numpy()
+        scl_h = eng.scl.cpu().numpy()
+        scl_vector = scl_h[y[:, 2].astype('int')]          # X_scl[feature * n_points, 0] (:576)
+        y0[:, 0] = (y[:, 0] - cnt_vector) / scl_vector
+        y0[:, 1] = y[:, 1] / scl_vector
+        self.cnt_vector = cnt_vector
+        self.scl_vector = scl_vector
+        return y0
+
+    def predict(self, y):
+        """OLS estimate of the POD coefficients from sparse measurements
+        (sparse_sensing.py:822-901).  Returns (Ar (N, r), Ar_sigma (N, r))."""
+        if isinstance(y, np.ndarray):
+            y = [y]
+        if not hasattr(self, 'Theta'):
+            raise AttributeError('The function fit has to be called '
+                                 'before calling predict.')
+        for yi in y:
+            if self.Theta.shape[0] != yi.shape[0]:
+                raise ValueError('The number of rows of Theta does not match the number'
+                                 ' of rows of y.')
+            if yi.shape[1] != 3:
+                raise ValueError('The y array has the wrong number of columns. y has'
+                                 ' to have dimensions (s,3).')
+        if self.method == 'COLS':
+            raise NotImplementedError('constrained OLS (cvxpy) is out of scope, SURVEY.md 8')
+        if self.method != 'OLS':
+            raise NotImplementedError('The prediction method selected has not been '
+                                      'implemented yet')
+        eng = self._engine()
+        N = len(y)
+        Y = np.stack([np.asarray(yi, dtype=np.float64) for yi in y])        # (N, s, 3)
+        Yd = torch.from_numpy(Y).to(eng.dev)
+        scl_s = eng.scl[Yd[:, :, 2].to(torch.int64)]                         # (N, s)
+        cnt_s = self._cnt_s
+        weighted = torch.any(Yd[:, :, 1] != 0, dim=1)                        # :868
+        Ar = torch.zeros(N, eng.r, dtype=torch.float64, device=eng.dev)
+        Asig = torch.zeros(N, eng.r, dtype=torch.float64, device=eng.dev)
+        plain = ~weighted
+        if bool(plain.any()):
+            idx = torch.nonzero(plain).flatten()
+            same_features = bool((Yd[idx, :, 2] == Yd[idx[0], :, 2]).all())
+            if same_features:
+                Ar[idx] = eng.ols_predict(Yd[idx, :, 0].contiguous(), cnt_s,
+                                          scl_s[idx[0]].contiguous(), self._PinvT)
+            else:
+                Y0 = (Yd[idx, :, 0] - cnt_s) / scl_s[idx]
+                Ar[idx] = eng.ols_predict(Y0.contiguous(), None, None, self._PinvT)
+        if bool(weighted.any()):                                             # :871-878
+            idx = torch.nonzero(weighted).flatten()
+            y0v = (Yd[idx, :, 0] - cnt_s) / scl_s[idx]
+            y0s = Yd[idx, :, 1] / scl_s[idx]
+            Wt = (1.0 / y0s).unsqueeze(2) * self._Theta_d.unsqueeze(0)       # diag(1/sigma) Theta
+            P = torch.linalg.pinv(Wt, rtol=1e-15)                            # (Nw, r, s)
+            Ar[idx] = torch.bmm(P, (y0v / y0s).unsqueeze(2)).squeeze(2)
+            Asig[idx] = torch.bmm(P, y0s.unsqueeze(2)).squeeze(2).abs()
+        self.scale_vector(y[-1])                # leaves cnt_vector / scl_vector like the reference
+        return Ar.cpu().numpy(), Asig.cpu().numpy()
+
+    def gem(self, *args, **kwargs):
+        raise NotImplementedError('GEM placement is a "next" row (SURVEY.md 8f)')

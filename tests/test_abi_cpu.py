@@ -1,0 +1,106 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol declared in
+include/omb200.h (no compute calls), and the host mirror raises the reference's errors before any
+device work (reference sparse_sensing.py:69-81, :314-333, :752-754)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from openmeasure_b200 import build
+    build.build()
+    from openmeasure_b200 import _lib
+    return _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "omb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(omb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    L = ctypes.CDLL(lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/omb200.h but not exported"
+
+
+def test_bindings_cover_the_header(lib):
+    assert sorted(lib.SIGNATURES) == _declared_symbols()
+    L = lib.load()
+    assert L.omb_version() >= 100
+    assert L.omb_launch_count() == 0
+
+
+def test_argument_errors_precede_device_work(lib):
+    L = lib.load()
+    rc = L.omb_row_means(None, 4, 4, None, None)
+    assert rc < 0 and b"null pointer" in L.omb_last_error()
+    rc = L.omb_qrcp(None, 16, 10, 4, 4, None, None, None, 1, 0, None, None, None, None)
+    assert rc < 0
+    assert L.omb_launch_count() == 0
+
+
+def test_constructor_and_mode_errors_match_reference():
+    from openmeasure_b200.sparse_sensing import ROM, SPR
+    X = np.zeros((6, 3))
+    with pytest.raises(TypeError):
+        ROM([[1.0, 2.0]], 1, None)
+    with pytest.raises(TypeError):
+        ROM(X, 2.0, None)
+    with pytest.raises(Exception):
+        SPR(X, 4, None)
+    rom = ROM(X, 2, None)
+    assert rom.n_points == 3 and rom.X is X
+    with pytest.raises(ValueError):
+        rom.fit(select_modes='variance', n_modes=101)
+    with pytest.raises(TypeError):
+        rom.fit(select_modes='number', n_modes=2.0)
+    with pytest.raises(ValueError):
+        rom.fit(select_modes='number', n_modes=4)
+    with pytest.raises(ValueError):
+        rom.fit(select_modes='bogus', n_modes=1)
+    ev = np.array([50.0, 90.0, 100.0])
+    U, A = rom.reduction(np.zeros((6, 3)), np.zeros((3, 3)), ev, 'variance', 80)
+    assert rom.r == 2 and U.shape == (6, 2) and A.shape == (3, 2)
+
+
+def test_sensor_matrix_supports_reference_idioms():
+    from openmeasure_b200.sparse_sensing import SensorMatrix
+    C = SensorMatrix([4, 0, 7], 9)
+    assert C.shape == (3, 9)
+    assert np.argmax(C[1, :]) == 0 and np.argmax(C[2, :]) == 7
+    x = np.arange(9.0) * 2
+    np.testing.assert_array_equal(C @ x, [8.0, 0.0, 14.0])
+    np.testing.assert_array_equal(C.dot(x), np.asarray(C) @ x)
+    dense = np.asarray(C)
+    assert dense.shape == (3, 9) and dense.sum() == 3 and dense[0, 4] == 1
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from openmeasure_b200 import _lib
+    from openmeasure_b200.sparse_sensing import SPR
+    spr = SPR(np.random.default_rng(0).random((20, 5)), 2, None)
+    with pytest.raises(_lib.OmbError):
+        spr.fit(n_modes=100)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "openmeasure_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle's", "").replace("oracle/csrc/oracle.c", "") \
+                    or f in ("synth.py",), f

@@ -1,0 +1,356 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the ROM-SPR mirror) against the CPU oracle,
+the reference's golden fixtures, and numpy/scipy themselves.  Tolerances follow BASELINE.json:
+pivots bit-exact on non-degenerate inputs, singular values and reconstructions 1e-10 relative,
+modes up to sign; centring/scaling bit-exact (the reference's own tests use assert_array_equal)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from openmeasure_b200 import build
+    build.build()
+    return torch
+
+
+def _sps():
+    from openmeasure_b200 import sparse_sensing
+    return sparse_sensing
+
+
+def _orth(n, r, seed):
+    rng = np.random.default_rng(seed)
+    w = 1.0 + 5.0 * rng.random((n, 1)) ** 4
+    Q, _ = np.linalg.qr(rng.standard_normal((n, r)) * w)
+    return Q
+
+
+def _sign_align(U, Uref):
+    s = np.sign(np.sum(U * Uref, axis=0))
+    s[s == 0] = 1
+    return U * s, s
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic generator: CUDA twin == CPU twin, bit for bit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,n_c,m,r,c0,ncl", [(3, 50, 17, 6, 0, 50), (9, 700, 41, 14, 100, 333),
+                                              (2, 300, 160, 20, 0, 300)])
+def test_synth_cuda_equals_cpu(torch_cuda, F, n_c, m, r, c0, ncl):
+    from openmeasure_b200 import synth as gsynth
+    from oracle import synth as osynth
+    Xg = gsynth.snapshots(F, n_c, m, r, cell0=c0, ncell_loc=ncl).cpu().numpy()
+    Xo = osynth.snapshots(F, n_c, m, r, cell0=c0, ncell_loc=ncl)
+    np.testing.assert_array_equal(Xg, Xo)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: centring / scaling, bit-exact vs numpy (mirrors reference tests/test_rom.py:19-46)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_pts,F,m", [(10, 2, 5), (1, 3, 4), (400, 3, 41), (77, 2, 129), (50, 2, 1024),
+                                       (3000, 4, 41), (7, 5, 300), (20000, 2, 33)])
+@pytest.mark.parametrize("scale_type", ["std", "pareto", "range"])
+def test_centering_and_scaling_bit_exact(torch_cuda, n_pts, F, m, scale_type):
+    rng = np.random.default_rng(n_pts * 31 + m)
+    X = rng.random((n_pts * F, m)) * 10.0 ** rng.integers(-2, 3, (n_pts * F, 1))
+    rom = _sps().ROM(X, F, None)
+    X0 = rom.scale_data(scale_type)
+    np.testing.assert_array_equal(rom.X_cnt, np.mean(X, axis=1)[:, np.newaxis])
+    X_scl = np.zeros((X.shape[0], 1))
+    for f in range(F):
+        blk = X[f * n_pts:(f + 1) * n_pts]
+        X_scl[f * n_pts:(f + 1) * n_pts] = {"std": np.std(blk), "pareto": np.sqrt(np.std(blk)),
+                                            "range": np.max(blk) - np.min(blk)}[scale_type]
+    np.testing.assert_array_equal(rom.X_scl, X_scl)
+    np.testing.assert_array_equal(X0, (X - np.mean(X, axis=1)[:, np.newaxis]) / X_scl)
+
+
+@pytest.mark.parametrize("scale_type", ["none", "vast", "level", "max", "variance", "poisson", "median",
+                                        "l2-norm"])
+def test_other_scalings_match_oracle(torch_cuda, scale_type):
+    from oracle import pod_oracle as po
+    rng = np.random.default_rng(5)
+    X = rng.random((3 * 211, 19)) + 0.25
+    rom = _sps().ROM(X, 3, None)
+    X0 = rom.scale_data(scale_type)
+    X0o, cnt, scl = po.center_scale(X, 3, scale_type, 1)
+    np.testing.assert_array_equal(rom.X_cnt, cnt)
+    np.testing.assert_allclose(rom.X_scl, scl, rtol=4e-16 if scale_type != "l2-norm" else 1e-13)
+    np.testing.assert_allclose(X0, X0o, rtol=1e-13, atol=1e-15)
+
+
+def test_centering_axis_none_bit_exact(torch_cuda):
+    rng = np.random.default_rng(9)
+    X = rng.random((2 * 1500, 23))
+    rom = _sps().ROM(X, 2, None)
+    rom.scale_data(axis_cnt=None)
+    X_cnt = np.zeros((X.shape[0], 1))
+    for f in range(2):
+        X_cnt[f * 1500:(f + 1) * 1500] = np.mean(X[f * 1500:(f + 1) * 1500])
+    np.testing.assert_array_equal(rom.X_cnt, X_cnt)
+
+
+def test_broken_options_raise_like_reference(torch_cuda):
+    X = np.random.default_rng(0).random((20, 5))
+    rom = _sps().ROM(X, 2, None)
+    with pytest.raises(ValueError):
+        rom.scale_data("vast_2")
+    with pytest.raises(ValueError):
+        rom.scale_data(axis_cnt=0)
+    with pytest.raises(NotImplementedError):
+        rom.scale_data("nonsense")
+
+
+# ---------------------------------------------------------------------------------------------
+# K6: pivoted QR kernel vs the C oracle (bitwise, block=1), scipy and the blocked variant
+# ---------------------------------------------------------------------------------------------
+def _gpu_qrcp(torch, Ur, block, s=None):
+    from openmeasure_b200 import engine
+    n, r = Ur.shape
+    eng = engine.Engine(torch.zeros(n, 1, dtype=torch.float64, device="cuda"), 1, group=False)
+    eng.set_basis_rows(torch.from_numpy(np.ascontiguousarray(Ur)).cuda())
+    piv, rdiag, gap = eng.qrcp(s=s, block=block)
+    return piv.cpu().numpy(), rdiag.cpu().numpy(), gap.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,r", [(20, 5), (50, 5), (2001, 14), (5000, 40), (6000, 100), (3001, 128),
+                                 (100000, 24)])
+def test_qrcp_unblocked_is_bitwise_dlaqp2(torch_cuda, n, r):
+    from oracle import clib
+    Ur = _orth(n, r, 7 * n + r)
+    o = clib.qrcp_dlaqp2(Ur)
+    piv, rdiag, gap = _gpu_qrcp(torch_cuda, Ur, block=1)
+    np.testing.assert_array_equal(piv, o["piv"])
+    np.testing.assert_array_equal(rdiag, o["rdiag"])           # bit-exact R diagonal
+    np.testing.assert_allclose(gap, o["gap"], rtol=0, atol=1e-12)
+    _, _, P = sla.qr(Ur.T, pivoting=True, mode="economic")
+    np.testing.assert_array_equal(piv, P[:r])                   # and LAPACK's pivots
+
+
+@pytest.mark.parametrize("n,r,block", [(50, 5, 2), (2001, 14, 4), (5000, 40, 8), (6000, 100, 8),
+                                       (6000, 100, 16), (3001, 128, 6), (100000, 24, 5)])
+def test_qrcp_blocked_matches_lapack_pivots(torch_cuda, n, r, block):
+    Ur = _orth(n, r, 7 * n + r)
+    _, R, P = sla.qr(Ur.T, pivoting=True, mode="economic")
+    piv, rdiag, _ = _gpu_qrcp(torch_cuda, Ur, block=block)
+    np.testing.assert_array_equal(piv, P[:r])
+    np.testing.assert_allclose(np.abs(rdiag), np.abs(np.diag(R)), rtol=1e-11)
+
+
+@pytest.mark.parametrize("block", [1, 4])
+def test_qrcp_exact_ties_follow_lapack_order(torch_cuda, block):
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        base = _orth(60, 6, seed)
+        Ur = np.concatenate([base, base[rng.permutation(60)[:30]], base], axis=0)
+        _, _, P = sla.qr(Ur.T, pivoting=True, mode="economic")
+        piv, _, gap = _gpu_qrcp(torch_cuda, Ur, block=block)
+        np.testing.assert_array_equal(piv, P[:6])
+        assert gap.min() == 0.0                                 # the meter reports the ties
+
+
+def test_qrcp_partial_steps_and_rank_deficient_columns(torch_cuda):
+    from oracle import clib
+    Ur = _orth(900, 12, 11)
+    Ur[100:400] = 0.0                                           # masked-out candidates
+    o = clib.qrcp_dlaqp2(Ur)
+    piv, rdiag, _ = _gpu_qrcp(torch_cuda, Ur, block=1)
+    np.testing.assert_array_equal(piv, o["piv"])
+    piv5, _, _ = _gpu_qrcp(torch_cuda, Ur, block=3, s=5)
+    np.testing.assert_array_equal(piv5, o["piv"][:5])
+
+
+# ---------------------------------------------------------------------------------------------
+# whole path vs the reference's golden fixtures (tests/golden, oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+def test_pipeline_matches_reference_golden(torch_cuda, golden):
+    g = golden
+    X = g["X"]
+    n, m = X.shape
+    n_c = n // g["F"]
+    spr = _sps().SPR(X.copy(), g["F"], np.zeros((n_c, 3)))
+    spr.fit(scale_type=g["scale_type"], axis_cnt=g["axis_cnt"], select_modes=g["select_modes"],
+            n_modes=g["n_modes"])
+    np.testing.assert_array_equal(spr.X_cnt, g["X_cnt"])
+    np.testing.assert_array_equal(spr.X_scl, g["X_scl"])
+    np.testing.assert_array_equal(spr.X0[:64], g["X0_head"])
+    assert spr.r == g["r"]
+    np.testing.assert_allclose(spr.Sigma_r, g["Sigma_r"], rtol=RTOL)
+    Ur, sgn = _sign_align(spr.Ur, g["Ur"])
+    # modes up to sign; a mode's accuracy scales with its neighbouring singular-value gap
+    np.testing.assert_allclose(Ur, g["Ur"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(spr.Ar * sgn, g["Ar"], rtol=0, atol=1e-9 * g["Sigma_r"][0])
+    C = spr.optimal_placement()
+    assert C.shape == (g["r"], n)
+    np.testing.assert_array_equal(spr.qr_pivots, g["piv"])      # bit-exact pivots
+    assert spr.qr_gap.min() > 1e-9
+    spr.train(C)
+    np.testing.assert_allclose(spr.Theta * sgn, g["Theta"], rtol=0, atol=1e-9)
+    Ar, Asig = spr.predict(list(g["Y"]))
+    Xrec = spr.reconstruct(Ar)
+    np.testing.assert_allclose(Xrec, g["X_rec"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(Ar * sgn, g["Ar_pred"], rtol=0, atol=1e-8 * np.abs(g["Ar_pred"]).max())
+    np.testing.assert_allclose(Asig, g["Ar_sigma"], rtol=0, atol=1e-8 * max(np.abs(g["Ar_sigma"]).max(), 1e-300))
+
+
+# ---------------------------------------------------------------------------------------------
+# mirrors of the reference's own unit tests (tests/test_rom.py, tests/test_spr.py), same shapes
+# ---------------------------------------------------------------------------------------------
+class TestReferenceUnitTests:
+    def setup_method(self, method):
+        rng = np.random.default_rng(12345)
+        self.n_points, self.n_features, self.m = 10, 2, 5
+        self.X = rng.random(size=(self.n_points * self.n_features, self.m))
+        self.xyz = rng.random(size=(self.n_points, 3))
+        self.C = np.eye(self.X.shape[0])
+
+    def test_decomposition_svd(self, torch_cuda):           # test_rom.py:48-55, up to sign
+        rom = _sps().ROM(self.X, self.n_features, self.xyz)
+        X0 = rom.scale_data()
+        U, Sigma, Vt = np.linalg.svd(X0, full_matrices=False)
+        A = np.dot(np.diag(Sigma), Vt).T
+        Ur, Ar, _ = rom.decomposition(X0, select_modes='number', n_modes=self.m - 1)
+        Ur, sgn = _sign_align(Ur, U[:, :self.m - 1])
+        np.testing.assert_allclose(Ur, U[:, :self.m - 1], atol=1e-10)
+        np.testing.assert_allclose(Ar * sgn, A[:, :self.m - 1], atol=1e-10)
+
+    def test_reduction_number_and_variance(self, torch_cuda):   # test_rom.py:57-65
+        rom = _sps().ROM(self.X, self.n_features, self.xyz)
+        X0 = rom.scale_data()
+        rom.decomposition(X0, select_modes='number', n_modes=self.m - 1)
+        assert rom.r == self.m - 1
+        rom.decomposition(X0, select_modes='variance', n_modes=100)
+        assert rom.r == self.m
+
+    def test_fit(self, torch_cuda):                           # test_rom.py:67-74
+        rom = _sps().ROM(self.X, self.n_features, self.xyz)
+        X0 = rom.scale_data()
+        _, Sigma, Vt = np.linalg.svd(X0, full_matrices=False)
+        rom.fit(n_modes=100)
+        k = self.m - 1                                        # mode m is rounding noise (row-centred)
+        V, _ = _sign_align(rom.Vr[:, :k], Vt.T[:, :k])
+        np.testing.assert_allclose(V, Vt.T[:, :k], atol=1e-9)
+        np.testing.assert_allclose(rom.Sigma_r[:k], Sigma[:k], rtol=RTOL)
+
+    def test_unscaling(self, torch_cuda):                     # test_rom.py:76-80
+        rom = _sps().ROM(self.X, self.n_features, self.xyz)
+        X0 = rom.scale_data()
+        rom.fit(n_modes=100)
+        np.testing.assert_allclose(rom.unscale_data(X0[:, 0]), rom.X[:, 0])
+
+    def test_reconstruction(self, torch_cuda):                # test_rom.py:82-85
+        rom = _sps().ROM(self.X, self.n_features, self.xyz)
+        rom.fit(n_modes=100)
+        np.testing.assert_allclose(rom.reconstruct(rom.Ar[0, :]), rom.X[:, [0]], rtol=RTOL)
+
+    def test_optimal_placement_qr(self, torch_cuda):          # test_spr.py:21-25
+        spr = _sps().SPR(self.X, self.n_features, self.xyz)
+        spr.fit(n_modes=100)
+        C_qr = spr.optimal_placement()
+        assert C_qr.shape[0] == self.m and C_qr.shape[1] == spr.X.shape[0]
+
+    def test_scale_vector_and_predict(self, torch_cuda):      # test_spr.py:27-60
+        spr = _sps().SPR(self.X, self.n_features, self.xyz)
+        X_cnt = np.mean(self.X, axis=1)[:, np.newaxis]
+        X_scl = np.zeros((self.X.shape[0], 1))
+        for f in range(self.n_features):
+            sl = slice(f * self.n_points, (f + 1) * self.n_points)
+            X_scl[sl] = np.std(self.X[sl])
+        spr.fit(n_modes=100)
+        spr.train(self.C)
+        y = np.zeros((self.C.shape[0], 3))
+        y[:, 0] = self.C @ self.X[:, 0]
+        for f in range(self.n_features):
+            y[f * self.n_points:(f + 1) * self.n_points, 2] = f
+        y0 = spr.scale_vector(y)
+        y0_check = np.zeros((self.C.shape[0], 2))
+        y0_check[:, 0] = (y[:, 0] - X_cnt[:, 0]) / X_scl[:, 0]
+        np.testing.assert_allclose(y0, y0_check)
+        a, _ = spr.predict(y)
+        np.testing.assert_allclose(spr.reconstruct(a), self.X[:, [0]])
+
+    def test_errors(self, torch_cuda):                        # sparse_sensing.py:752-754, :791-803, :848-854
+        spr = _sps().SPR(self.X, self.n_features, self.xyz)
+        spr.fit(select_modes='number', n_modes=3)
+        with pytest.raises(NotImplementedError):
+            spr.optimal_placement(calc_type='bogus')
+        with pytest.raises(ValueError):
+            spr.train(np.eye(7))
+        spr.train(spr.optimal_placement())
+        with pytest.raises(ValueError):
+            spr.predict(np.zeros((4, 3)))
+        with pytest.raises(ValueError):
+            spr.predict(np.zeros((3, 2)))
+
+
+# ---------------------------------------------------------------------------------------------
+# mask quirk (the basis is zeroed in place), general dense C, basis= resume hook
+# ---------------------------------------------------------------------------------------------
+def test_mask_basis_dense_c(torch_cuda):
+    from oracle import pod_oracle as po, synth as osynth
+    X = osynth.snapshots(3, 500, 20, 8)
+    n = X.shape[0]
+    f = po.fit(X, 3, n_modes=8, select_modes="number")
+    spr = _sps().SPR(X, 3, None)
+    spr.fit(select_modes='number', n_modes=8)
+    mask = np.ones(n, dtype=bool)
+    mask[200:900] = False
+    piv_ref = po.qr_pivots(f["Ur"], mask)
+    C = spr.optimal_placement(mask=mask)
+    np.testing.assert_array_equal(np.argmax(np.asarray(C), axis=1), piv_ref)
+    assert np.all(spr.Ur[~mask] == 0)                          # reference quirk :737-738
+    # general (non one-hot) dense C goes through the dense product
+    rng = np.random.default_rng(0)
+    Cd = rng.random((12, n))
+    spr.train(Cd)
+    np.testing.assert_allclose(spr.Theta, Cd @ spr.Ur, rtol=1e-12, atol=1e-14)
+    # resume from a given basis (sparse_sensing.py:493-497)
+    spr2 = _sps().SPR(X, 3, None)
+    spr2.fit(basis=(f["Ur"], f["Ar"]))
+    assert spr2.r == 8
+    np.testing.assert_array_equal(spr2.Ur, f["Ur"])
+    C2 = spr2.optimal_placement(block=1)
+    np.testing.assert_array_equal(spr2.qr_pivots, po.qr_pivots(f["Ur"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at a config-2-like size (oracle too slow to run in full here)
+# ---------------------------------------------------------------------------------------------
+def test_large_properties(torch_cuda):
+    from openmeasure_b200 import synth as gsynth
+    from oracle import clib
+    torch = torch_cuda
+    F, n_c, m, r = 9, 60000, 41, 40
+    Xd = gsynth.snapshots(F, n_c, m, r)
+    spr = _sps().SPR.from_device(Xd, F)
+    spr.fit(select_modes='number', n_modes=r)
+    U = spr._eng.basis_rows()
+    G = (U.T @ U).cpu().numpy()
+    np.testing.assert_allclose(G, np.eye(r), atol=1e-9)        # orthonormal modes
+    assert spr.pod_rel_err_bound < 1e-10
+    C = spr.optimal_placement()
+    o = clib.qrcp_dlaqp2(U.cpu().numpy())                       # oracle QRCP on the GPU's own basis
+    np.testing.assert_array_equal(spr.qr_pivots, o["piv"])
+    np.testing.assert_allclose(np.abs(spr.qr_rdiag), np.abs(o["rdiag"]), rtol=1e-11)
+    spr.train(C)
+    # snapshot 3 sampled at the sensors -> reconstruct: error bounded by the truncated energy
+    x = Xd[:, 3].cpu().numpy()
+    y = np.zeros((r, 3))
+    y[:, 0] = x[spr.qr_pivots]
+    y[:, 2] = spr.qr_pivots // n_c
+    a, _ = spr.predict(y)
+    xr = spr.reconstruct(a)[:, 0]
+    assert np.linalg.norm(xr - x) / np.linalg.norm(x) < 1e-3
+    # linearity of predict/reconstruct in the measurements (about the centring)
+    y2 = y.copy()
+    y2[:, 0] = 2 * y[:, 0] - spr.X_cnt[spr.qr_pivots, 0]
+    a2, _ = spr.predict(y2)
+    np.testing.assert_allclose(a2, 2 * a, rtol=1e-9, atol=1e-9 * np.abs(a).max())
