@@ -15,8 +15,10 @@
  *   - return value: 0 ok, <0 invalid argument, >0 cudaError_t; omb_last_error() gives the text;
  *   - snapshot layout: X is (F * n_c) x m, C-order FP64 (row = m contiguous snapshots), feature
  *     block f = rows [f*n_c, (f+1)*n_c)  (sparse_sensing.py:110);
- *   - basis layout: "mode-major" Ut is r x ld (ld >= n, ld % 2 == 0), Ut[q*ld + i] = U_r[i, q],
- *     so that the n candidate locations are the coalesced axis of every placement kernel.
+ *   - basis layout: "tiled mode-major": the n candidate rows are cut into tiles of 128 and a tile
+ *     stores its r modes back to back, Ut[(i/128)*r*128 + q*128 + i%128] = U_r[i, q]; the buffer
+ *     holds ceil(n/128) tiles (padding rows are zero).  The candidates are the coalesced axis of
+ *     every placement kernel and the trailing rows of a tile are one contiguous burst in HBM.
  */
 #ifndef OMB200_H
 #define OMB200_H
@@ -88,31 +90,33 @@ int omb_gram_combine(const double* d_Gf, int64_t F, int64_t m, const double* d_s
  *      with the initial QRCP column norms vn[i] = ||U_r[i,:]||_2 fused (replaces U = Q*U_R inside
  *      dgesdd and the dnrm2 initialisation of dgeqp3). d_vn may be NULL. -------------------- */
 int omb_backproject(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
-                    const double* d_scl, const double* d_W, int64_t r, double* d_Ut, int64_t ld,
-                    double* d_vn, void* stream);
+                    const double* d_scl, const double* d_W, int64_t r, double* d_Ut, double* d_vn,
+                    void* stream);
 
 /* ---- K6: QR with column pivoting over the n candidate locations (replaces
  *      scipy.linalg.qr(self.Ur.T, pivoting=True) -> LAPACK dgeqp3/dlaqp2, sparse_sensing.py:739).
- * d_Ut   r x ld mode-major basis (read only), d_vn initial norms (NULL -> computed here),
- * d_work r x ld scratch for the trailing matrix, d_ws omb_qrcp_ws_bytes() bytes,
- * block  = steps between trailing-matrix rewrites (1 = LAPACK's unblocked dlaqp2 arithmetic),
+ * d_Ut   tiled mode-major basis (read only), d_vn initial norms (NULL -> computed here; else
+ *        ceil(n/128)*128 doubles), d_work scratch of the same size as d_Ut for the trailing
+ *        matrix, d_ws omb_qrcp_ws_bytes() bytes,
+ * block  = steps (1..8) between trailing-matrix rewrites; 1 = LAPACK's unblocked dlaqp2
+ *        arithmetic, bit for bit, for r <= 100,
  * outputs (device): d_piv[s] global row indices in selection order (+ index_base), d_rdiag[s] =
  * R[k,k], d_gap[s] = relative gap between the best and second-best candidate norm (degeneracy
- * meter).  `valid` (NULL or n bytes, 0 = excluded) implements optimal_placement(mask=...). */
+ * meter).  optimal_placement(mask=...) zeroes the excluded rows of the basis beforehand, exactly
+ * like the reference (:737-738).  One placement at a time per device. */
 int64_t omb_qrcp_ws_bytes(int64_t n, int64_t r);
-int omb_qrcp(const double* d_Ut, int64_t ld, int64_t n, int64_t r, int64_t s, const double* d_vn,
-             double* d_work, void* d_ws, int block, int64_t index_base, int64_t* d_piv,
-             double* d_rdiag, double* d_gap, void* stream);
+int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
+             void* d_ws, int block, int64_t index_base, int64_t* d_piv, double* d_rdiag,
+             double* d_gap, void* stream);
 
 /* ---- K8/K9: train = row gather (replaces the dense C.dot(Ur), C.dot(X_cnt);
  *      sparse_sensing.py:797, :573).  d_Theta is s x r row-major, d_cnt_s may be NULL. -------- */
-int omb_gather_rows(const double* d_Ut, int64_t ld, int64_t r, const int64_t* d_piv, int64_t s,
+int omb_gather_rows(const double* d_Ut, int64_t r, const int64_t* d_piv, int64_t s,
                     double* d_Theta, const double* d_cnt, double* d_cnt_s, void* stream);
 /* Ur (n x r, C-order) <- Ut, and back (for the .Ur attribute / fit(basis=...) / mask) */
-int omb_modes_to_rows(const double* d_Ut, int64_t ld, int64_t n, int64_t r, double* d_Ur,
+int omb_modes_to_rows(const double* d_Ut, int64_t n, int64_t r, double* d_Ur, void* stream);
+int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, double* d_vn,
                       void* stream);
-int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, int64_t ld,
-                      double* d_vn, void* stream);
 
 /* ---- K10: batched OLS predict (replaces the per-vector np.linalg.pinv + dot loop,
  *      sparse_sensing.py:865-878 with all sigma == 0):
@@ -124,7 +128,7 @@ int omb_ols_predict(const double* d_Y, const double* d_cnt_s, const double* d_sc
 /* ---- K11: reconstruct rows [row0, row0+nrows) of X_rec = U_r A^T, unscaled in the epilogue
  *      out[i, k] = scl[f(i)] * acc + cnt[i]  (replaces Ur @ Ar.T + the per-column unscale_data,
  *      sparse_sensing.py:371-373, :235).  d_out is nrows x N row-major.  d_cnt/d_scl may be NULL. */
-int omb_reconstruct(const double* d_Ut, int64_t ld, int64_t r, const double* d_A, int64_t N,
+int omb_reconstruct(const double* d_Ut, int64_t n, int64_t r, const double* d_A, int64_t N,
                     const double* d_cnt, const double* d_scl, int64_t n_c, int64_t row0,
                     int64_t nrows, double* d_out, void* stream);
 

@@ -24,12 +24,12 @@ SIGNATURES = {
     "omb_gram_ws_bytes": (_i64, [_i64, _i64, _i64]),
     "omb_gram": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "omb_gram_combine": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
-    "omb_backproject": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "omb_backproject": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "omb_qrcp_ws_bytes": (_i64, [_i64, _i64]),
-    "omb_qrcp": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
-    "omb_gather_rows": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
-    "omb_modes_to_rows": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
-    "omb_rows_to_modes": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "omb_qrcp": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
+    "omb_gather_rows": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "omb_modes_to_rows": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "omb_rows_to_modes": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "omb_ols_predict": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "omb_reconstruct": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
 }

@@ -2,7 +2,7 @@
 //
 // Replaces the U = Q * U_R product inside LAPACK dgesdd behind np.linalg.svd (reference
 // sparse_sensing.py:272) and the slice U[:, :r] (:336).  X0 = (X - cnt)/scl is formed on the fly
-// (never materialised); the result is written mode-major (r x ld) -- the layout the placement
+// (never materialised); the result is written tiled mode-major (common.cuh: Ut[tile][q][128]) -- the layout the placement
 // kernels stream -- and the initial dgeqp3 column norms ||U_r[i, :]||_2 are produced in the same
 // epilogue, summed sequentially over the modes with fma (the oracle's nrm2 order).
 // Tensor path: DMMA.8x8x4 (mma.sync m8n8k4 f64).
@@ -31,7 +31,7 @@ template <int QB>
 __global__ void __launch_bounds__(BP_THREADS)
 backproject_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, const double* __restrict__ cnt,
                    const double* __restrict__ scl, const double* __restrict__ W, int r,
-                   double* __restrict__ Ut, int64_t ld, double* __restrict__ vn)
+                   double* __restrict__ Ut, double* __restrict__ vn)
 {
     using S = BpSmem<QB>;
     extern __shared__ double smem[];
@@ -108,7 +108,7 @@ backproject_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, 
             const int qn = (r - q0) < S::QC ? (r - q0) : S::QC;
             for (int e = threadIdx.x; e < qn * BP_RT; e += BP_THREADS) {
                 const int qq = e / BP_RT, i = e - qq * BP_RT;
-                if (row0 + i < n) stg_stream(Ut + (int64_t)(q0 + qq) * ld + row0 + i, sC[qq * BP_LDC + i]);
+                if (row0 + i < n) stg_stream(Ut + basis_index(q0 + qq, row0 + i, r), sC[qq * BP_LDC + i]);
             }
             if (vn && threadIdx.x < BP_RT) {
                 for (int qq = 0; qq < qn; ++qq) {
@@ -124,7 +124,7 @@ backproject_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, 
 
 template <int QB>
 static int launch_bp(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl,
-                     const double* W, int r, double* Ut, int64_t ld, double* vn, cudaStream_t st)
+                     const double* W, int r, double* Ut, double* vn, cudaStream_t st)
 {
     using S = BpSmem<QB>;
     OMB_CUDA(cudaFuncSetAttribute(backproject_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -132,7 +132,7 @@ static int launch_bp(const double* X, int64_t n, int64_t n_c, int m, const doubl
     int64_t grid = ceil_div(n, BP_RT);
     int64_t cap = (int64_t)sm_count() * 24;
     if (grid > cap) grid = cap;
-    backproject_kernel<QB><<<(unsigned)grid, BP_THREADS, S::BYTES, st>>>(X, n, n_c, m, cnt, scl, W, r, Ut, ld, vn);
+    backproject_kernel<QB><<<(unsigned)grid, BP_THREADS, S::BYTES, st>>>(X, n, n_c, m, cnt, scl, W, r, Ut, vn);
     return check_launch("backproject_kernel");
 }
 
@@ -141,15 +141,14 @@ static int launch_bp(const double* X, int64_t n, int64_t n_c, int m, const doubl
 using namespace omb;
 
 extern "C" int omb_backproject(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
-                               const double* d_scl, const double* d_W, int64_t r, double* d_Ut, int64_t ld,
-                               double* d_vn, void* stream)
+                               const double* d_scl, const double* d_W, int64_t r, double* d_Ut, double* d_vn,
+                               void* stream)
 {
     OMB_CHECK_ARG(d_X && d_W && d_Ut, "null pointer");
     OMB_CHECK_ARG(F > 0 && n_c > 0 && m > 0 && r > 0, "non-positive size");
     const int64_t n = F * n_c;
-    OMB_CHECK_ARG(ld >= n, "ld < n");
     OMB_CHECK_ARG(m <= (1 << 20) && r <= (1 << 20), "m or r too large");
     cudaStream_t st = (cudaStream_t)stream;
-    if (r <= 64) return launch_bp<8>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, ld, d_vn, st);
-    return launch_bp<16>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, ld, d_vn, st);
+    if (r <= 64) return launch_bp<8>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
+    return launch_bp<16>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
 }

@@ -31,6 +31,16 @@ __host__ __device__ static inline int64_t round_up(int64_t a, int64_t b) { retur
 
 int sm_count();
 
+// Basis layout ("tiled mode-major"): the n candidate rows are cut into tiles of OMB_TB; a tile
+// stores its r modes back to back, Ut[tile][q][OMB_TB].  Every pass over the trailing rows
+// [i0, r) of a tile is then ONE contiguous (r - i0) * OMB_TB * 8-byte burst in HBM.
+constexpr int OMB_TB = 128;
+__host__ __device__ static inline int64_t basis_tiles(int64_t n) { return (n + OMB_TB - 1) / OMB_TB; }
+__host__ __device__ static inline int64_t basis_index(int64_t q, int64_t j, int64_t r)
+{
+    return (j >> 7) * (r << 7) + (q << 7) + (j & (OMB_TB - 1));
+}
+
 // streaming (evict-first) 128-bit and 64-bit global accesses for data touched once per pass
 __device__ __forceinline__ double2 ldg_stream2(const double* p)
 {

@@ -13,14 +13,14 @@
 
 namespace omb {
 
-__global__ void gather_rows_kernel(const double* __restrict__ Ut, int64_t ld, int r, const int64_t* __restrict__ piv,
+__global__ void gather_rows_kernel(const double* __restrict__ Ut, int r, const int64_t* __restrict__ piv,
                                    int s, double* __restrict__ Theta, const double* __restrict__ cnt,
                                    double* __restrict__ cnt_s)
 {
     const int total = s * r;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int a = e / r, q = e - a * r;
-        Theta[e] = Ut[(int64_t)q * ld + piv[a]];
+        Theta[e] = Ut[basis_index(q, piv[a], r)];
     }
     if (cnt && cnt_s)
         for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < s; a += gridDim.x * blockDim.x)
@@ -29,7 +29,7 @@ __global__ void gather_rows_kernel(const double* __restrict__ Ut, int64_t ld, in
 
 // Ur[i][q] = Ut[q][i]   (32 x 32 tiles through shared memory)
 __global__ void __launch_bounds__(256)
-modes_to_rows_kernel(const double* __restrict__ Ut, int64_t ld, int64_t n, int r, double* __restrict__ Ur)
+modes_to_rows_kernel(const double* __restrict__ Ut, int64_t n, int r, double* __restrict__ Ur)
 {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
@@ -41,7 +41,7 @@ modes_to_rows_kernel(const double* __restrict__ Ut, int64_t ld, int64_t n, int r
         for (int yy = ty; yy < 32; yy += 8) {
             const int q = q0 + yy;
             const int64_t i = i0 + tx;
-            tile[yy][tx] = (q < r && i < n) ? Ut[(int64_t)q * ld + i] : 0.0;
+            tile[yy][tx] = (q < r && i < n) ? Ut[basis_index(q, i, r)] : 0.0;
         }
         __syncthreads();
         for (int yy = ty; yy < 32; yy += 8) {
@@ -55,7 +55,7 @@ modes_to_rows_kernel(const double* __restrict__ Ut, int64_t ld, int64_t n, int r
 
 // Ut[q][i] = Ur[i][q]; optional row norms (sequential fma over q, the oracle's dnrm2 order)
 __global__ void __launch_bounds__(256)
-rows_to_modes_kernel(const double* __restrict__ Ur, int64_t n, int r, double* __restrict__ Ut, int64_t ld)
+rows_to_modes_kernel(const double* __restrict__ Ur, int64_t n, int r, double* __restrict__ Ut)
 {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -73,18 +73,18 @@ rows_to_modes_kernel(const double* __restrict__ Ur, int64_t n, int r, double* __
         for (int yy = ty; yy < 32; yy += 8) {
             const int q = q0 + yy;
             const int64_t i = i0 + tx;
-            if (q < r && i < n) Ut[(int64_t)q * ld + i] = tile[tx][yy];
+            if (q < r && i < n) Ut[basis_index(q, i, r)] = tile[tx][yy];
         }
         __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(256)
-row_norms_kernel(const double* __restrict__ Ut, int64_t ld, int64_t n, int r, double* __restrict__ vn)
+row_norms_kernel(const double* __restrict__ Ut, int64_t n, int r, double* __restrict__ vn)
 {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int k = 0; k < r; ++k) { const double x = Ut[(int64_t)k * ld + j]; s = fma(x, x, s); }
+        for (int k = 0; k < r; ++k) { const double x = Ut[basis_index(k, j, r)]; s = fma(x, x, s); }
         vn[j] = sqrt(s);
     }
 }
@@ -148,7 +148,7 @@ ols_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, int6
                     const int kk = e / OT, ii = e - kk * OT;
                     const int k = k0 + kk;
                     const int64_t i = i0 + ii;
-                    sA[kk * O_LD + ii] = (k < K && i < M) ? A[(int64_t)k * lda + row0 + i] : 0.0;
+                    sA[kk * O_LD + ii] = (k < K && i < M) ? A[basis_index(k, row0 + i, K)] : 0.0;
                 }
                 for (int e = threadIdx.x; e < OT * OK_; e += O_THREADS) {
                     const int jj = e / OK_, kk = e - jj * OK_;
@@ -205,40 +205,39 @@ ols_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, int6
 
 using namespace omb;
 
-extern "C" int omb_gather_rows(const double* d_Ut, int64_t ld, int64_t r, const int64_t* d_piv, int64_t s,
+extern "C" int omb_gather_rows(const double* d_Ut, int64_t r, const int64_t* d_piv, int64_t s,
                                double* d_Theta, const double* d_cnt, double* d_cnt_s, void* stream)
 {
     OMB_CHECK_ARG(d_Ut && d_piv && d_Theta, "null pointer");
     OMB_CHECK_ARG(r > 0 && s > 0 && s * r < (1ll << 30), "bad size");
     int g = (int)ceil_div(s * r, 256);
     if (g > 1024) g = 1024;
-    gather_rows_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(d_Ut, ld, (int)r, d_piv, (int)s, d_Theta, d_cnt, d_cnt_s);
+    gather_rows_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(d_Ut, (int)r, d_piv, (int)s, d_Theta, d_cnt, d_cnt_s);
     return check_launch("gather_rows_kernel");
 }
 
-extern "C" int omb_modes_to_rows(const double* d_Ut, int64_t ld, int64_t n, int64_t r, double* d_Ur, void* stream)
+extern "C" int omb_modes_to_rows(const double* d_Ut, int64_t n, int64_t r, double* d_Ur, void* stream)
 {
     OMB_CHECK_ARG(d_Ut && d_Ur, "null pointer");
-    OMB_CHECK_ARG(n > 0 && r > 0 && ld >= n, "bad size");
+    OMB_CHECK_ARG(n > 0 && r > 0, "bad size");
     int64_t g = ceil_div(n, 32) * ceil_div(r, 32);
     if (g > (int64_t)sm_count() * 32) g = (int64_t)sm_count() * 32;
-    modes_to_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_Ut, ld, n, (int)r, d_Ur);
+    modes_to_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_Ut, n, (int)r, d_Ur);
     return check_launch("modes_to_rows_kernel");
 }
 
-extern "C" int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, int64_t ld, double* d_vn,
-                                 void* stream)
+extern "C" int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, double* d_vn, void* stream)
 {
     OMB_CHECK_ARG(d_Ur && d_Ut, "null pointer");
-    OMB_CHECK_ARG(n > 0 && r > 0 && ld >= n, "bad size");
+    OMB_CHECK_ARG(n > 0 && r > 0, "bad size");
     int64_t g = ceil_div(n, 32) * ceil_div(r, 32);
     if (g > (int64_t)sm_count() * 32) g = (int64_t)sm_count() * 32;
-    rows_to_modes_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_Ur, n, (int)r, d_Ut, ld);
+    rows_to_modes_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_Ur, n, (int)r, d_Ut);
     int rc = check_launch("rows_to_modes_kernel");
     if (rc || !d_vn) return rc;
     int64_t g2 = ceil_div(n, 256);
     if (g2 > (int64_t)sm_count() * 8) g2 = (int64_t)sm_count() * 8;
-    row_norms_kernel<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_Ut, ld, n, (int)r, d_vn);
+    row_norms_kernel<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_Ut, n, (int)r, d_vn);
     return check_launch("row_norms_kernel");
 }
 
@@ -254,16 +253,16 @@ extern "C" int omb_ols_predict(const double* d_Y, const double* d_cnt_s, const d
     return check_launch("ols_gemm_kernel<predict>");
 }
 
-extern "C" int omb_reconstruct(const double* d_Ut, int64_t ld, int64_t r, const double* d_A, int64_t N,
+extern "C" int omb_reconstruct(const double* d_Ut, int64_t n, int64_t r, const double* d_A, int64_t N,
                                const double* d_cnt, const double* d_scl, int64_t n_c, int64_t row0, int64_t nrows,
                                double* d_out, void* stream)
 {
     OMB_CHECK_ARG(d_Ut && d_A && d_out, "null pointer");
     OMB_CHECK_ARG(N > 0 && r > 0 && nrows > 0 && row0 >= 0 && n_c > 0 && r < (1 << 24), "bad size");
-    OMB_CHECK_ARG(row0 + nrows <= ld, "row range exceeds ld");
+    OMB_CHECK_ARG(row0 + nrows <= n, "row range exceeds n");
     int64_t tiles = ceil_div(nrows, OT) * ceil_div(N, OT);
     if (tiles > (int64_t)sm_count() * 8) tiles = (int64_t)sm_count() * 8;
-    ols_gemm_kernel<1><<<(unsigned)tiles, O_THREADS, 0, (cudaStream_t)stream>>>(d_Ut, d_A, nrows, N, (int)r, ld, d_cnt,
+    ols_gemm_kernel<1><<<(unsigned)tiles, O_THREADS, 0, (cudaStream_t)stream>>>(d_Ut, d_A, nrows, N, (int)r, 0, d_cnt,
                                                                                  d_scl, n_c, row0, d_out);
     return check_launch("ols_gemm_kernel<reconstruct>");
 }

@@ -4,34 +4,35 @@
 // sparse_sensing.py:739), i.e. LAPACK dgeqp3 -> dlaqp2 (+ dlarfg / dlarf) on the r x n matrix
 // A = Ur^T, of which the reference keeps only the first r pivots (:741-743).
 //
-// Layout: A is mode-major (r rows of ld doubles), so the n candidates are the coalesced axis and
-// step i only touches rows i..r-1.  One thread owns one candidate column per step; the only
-// cross-thread work is the (norm, LAPACK-position) argmax.  Per step:
+// Layout: A is tiled mode-major, A[tile][q][128] (common.cuh): the trailing rows [i0, r) of the
+// 128 candidates of a tile are one contiguous burst.  One thread (or one DMMA fragment slot) owns
+// one candidate column per step; the only cross-thread work is the (norm, LAPACK-position) argmax.
+// Per pivot step:
 //
 //   panel kernel (1 CTA)   reduce the per-CTA argmax records -> pivot p; LAPACK's column-swap
 //                          bookkeeping (position keys for tie-breaking); gather p's trailing
-//                          column; dlarfg -> (v, tau, beta); for blocked runs the compact-WY T
-//                          and the row vector q = Q e_t.
-//   pass kernel (grid)     block == 1 or last step of a block: apply the block's reflectors to
-//                          every column (dlarf arithmetic, sequential fma), write the rows below
-//                          the block, down-date vn1/vn2 exactly like dlaqp2 (tol3z guard and norm
-//                          recomputation), emit the next argmax records.
-//                          inside a block: read-only GEMV  R[i, j] = q . A[i0:, j]  + down-date +
-//                          argmax: the trailing matrix is streamed once and never written.
+//                          column; dlarfg -> (v, tau, beta); compact-WY T and q = Q e_t.
+//   pass kernel (grid)     inside a block: read-only GEMV  R[i, j] = q . A[i0:, j]  + dlaqp2's
+//                          norm down-date (tol3z guard, exact recomputation) + next argmax: the
+//                          trailing matrix is streamed once and never written.
+//                          last step of a block: apply the block's reflectors to every column,
+//                          write the rows below the block, down-date, argmax.
+//                            block == 1: dlarf arithmetic in registers, the very fma sequence of
+//                                        oracle/csrc/oracle.c -> bit-identical to dlaqp2;
+//                            block  > 1: compact WY on the FP64 tensor path (DMMA.8x8x4).
 //
-// With block == 1 the arithmetic is dlaqp2's, operation for operation, in the order fixed by
-// oracle/csrc/oracle.c (bit-identical R diagonal, norms and pivots).  block > 1 moves
-// ~ (1 + 1/block)/2 of the bytes; pivots are identical on non-degenerate inputs (the degeneracy
-// meter d_gap reports how close any decision was).
+// block > 1 moves ~ (1 + 1/block)/2 of the bytes of the unblocked algorithm; pivots are identical
+// on non-degenerate inputs (the degeneracy meter d_gap reports how close any decision was).
 #include "common.cuh"
 #include "../../include/omb200.h"
 
 namespace omb {
 
 constexpr int QR_RMAX = 256;     // max modes (rows of A)
-constexpr int QR_BMAX = 16;      // max steps per block
+constexpr int QR_BMAX = 8;       // max steps per block
 constexpr int QR_NCAND = 4096;   // max CTAs of a pass kernel (argmax records)
 constexpr double QR_TOL3Z = 1.0536712127723509e-08;   // sqrt(2^-53), LAPACK tol3z
+constexpr int QR_LREG = 100;     // tallest trailing block of the register-resident (bit-exact) pass
 
 struct Cand {
     double best;      // largest partial column norm (-1: none)
@@ -76,6 +77,12 @@ __device__ __forceinline__ Cand cand_shfl_xor(const Cand& a, int o)
     b.key = __shfl_xor_sync(0xFFFFFFFFu, a.key, o);
     return b;
 }
+__device__ __forceinline__ Cand cand_empty()
+{
+    Cand c;
+    c.best = -1.0; c.second = -1.0; c.idx = -1; c.key = INT64_MAX;
+    return c;
+}
 // CTA-wide reduction; result valid in thread 0.  s_c must hold blockDim.x/32 records.
 __device__ __forceinline__ Cand cand_block_reduce(Cand c, Cand* s_c)
 {
@@ -107,11 +114,12 @@ __device__ __forceinline__ bool downdate(double rij, double& v1, double v2)
 // initial norms (when the back-projection did not supply them): sequential fma over the modes
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-qr_norms_kernel(const double* __restrict__ A, int64_t ld, int64_t n, int r, double* __restrict__ vn)
+qr_norms_kernel(const double* __restrict__ A, int64_t n, int r, double* __restrict__ vn)
 {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const double* col = A + basis_index(0, j, r);
         double s = 0.0;
-        for (int k = 0; k < r; ++k) { double x = ldg_stream(A + (int64_t)k * ld + j); s = fma(x, x, s); }
+        for (int k = 0; k < r; ++k) { double x = ldg_stream(col + (int64_t)k * OMB_TB); s = fma(x, x, s); }
         vn[j] = sqrt(s);
     }
 }
@@ -131,12 +139,13 @@ qr_init_kernel(const double* __restrict__ vn, int64_t n, double* __restrict__ vn
 
 // ---------------------------------------------------------------------------------------------
 // slow path of the read-only pass: exact trailing norm of one column after reflectors 0..t
+// (col points at the column's first trailing row; rows are OMB_TB apart)
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ double recompute_norm(const double* __restrict__ src, int64_t ld, int64_t j, int L, int t,
+__device__ __noinline__ double recompute_norm(const double* __restrict__ col, int L, int t,
                                               const double* __restrict__ Vg, const double* __restrict__ taug)
 {
     double c[QR_RMAX];
-    for (int k = 0; k < L; ++k) c[k] = src[(int64_t)k * ld + j];
+    for (int k = 0; k < L; ++k) c[k] = col[(int64_t)k * OMB_TB];
     for (int tt = 0; tt <= t; ++tt) {
         const double* v = Vg + tt * QR_RMAX;
         double w = c[tt];
@@ -152,12 +161,12 @@ __device__ __noinline__ double recompute_norm(const double* __restrict__ src, in
 
 // ---------------------------------------------------------------------------------------------
 // read-only pass: R[i, j] = q . A[i0:, j], down-date, argmax.  L = r - i0 rows (0 = argmax only).
-// Two adjacent columns per thread (128-bit loads).
+// Two adjacent columns per thread (128-bit loads); 64 threads sweep one tile's contiguous burst.
 // ---------------------------------------------------------------------------------------------
 constexpr int GV_THREADS = 256;
 
 __global__ void __launch_bounds__(GV_THREADS)
-qr_gemv_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int L, int t, int last_row,
+qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, int t, int last_row,
                const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
                int64_t s_total, Cand* __restrict__ cand)
 {
@@ -166,25 +175,24 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int L, int
     for (int k = threadIdx.x; k < L; k += GV_THREADS) s_q[k] = P->q[k];
     __syncthreads();
 
-    Cand best;
-    best.best = -1.0; best.second = -1.0; best.idx = -1; best.key = INT64_MAX;
-
-    const int64_t npairs = (n + 1) >> 1;
+    Cand best = cand_empty();
+    const int64_t npairs = basis_tiles(n) * (OMB_TB / 2);
     for (int64_t pr = (int64_t)blockIdx.x * GV_THREADS + threadIdx.x; pr < npairs;
          pr += (int64_t)gridDim.x * GV_THREADS) {
         const int64_t j = pr * 2;
+        if (j >= n) continue;
         double y0 = 0.0, y1 = 0.0;
-        const double* col = src + j;
+        const double* col = src + basis_index(i0, j, r);
         int k = 0;
         for (; k + 8 <= L; k += 8) {
             double2 a[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = ldg_stream2(col + (int64_t)(k + u) * ld);
+            for (int u = 0; u < 8; ++u) a[u] = ldg_stream2(col + (int64_t)(k + u) * OMB_TB);
 #pragma unroll
             for (int u = 0; u < 8; ++u) { y0 = fma(s_q[k + u], a[u].x, y0); y1 = fma(s_q[k + u], a[u].y, y1); }
         }
         for (; k < L; ++k) {
-            double2 a = ldg_stream2(col + (int64_t)k * ld);
+            double2 a = ldg_stream2(col + (int64_t)k * OMB_TB);
             y0 = fma(s_q[k], a.x, y0);
             y1 = fma(s_q[k], a.y, y1);
         }
@@ -197,7 +205,7 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int L, int
             if (v1 != 0.0 && L > 0) {
                 const double v2 = vn2[jj];
                 if (downdate(e ? y1 : y0, v1, v2)) {
-                    v1 = last_row ? 0.0 : recompute_norm(src, ld, jj, L, t, &P->V[0][0], P->tau);
+                    v1 = last_row ? 0.0 : recompute_norm(col + e, L, t, &P->V[0][0], P->tau);
                     vn2[jj] = v1;
                 }
                 vn1[jj] = v1;
@@ -211,71 +219,226 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int L, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// apply pass: apply reflectors 0..t of the current block to every column (dlarf arithmetic),
-// write rows t+1.. of the block-local tail to dst, down-date, argmax.
-// One thread per column; the column tail lives in shared memory (per-thread private slice).
+// unblocked apply pass (block == 1), register-resident: one thread owns one column tail of up to
+// LMAX rows and applies dlarf:  w = v^T c ; c -= tau w v  -- the fma sequence of the oracle, so
+// the trailing matrix, the norms and the pivots are bit-identical to dlaqp2.  v lives in shared
+// memory (one broadcast LDS per fma; this pass is HBM-bound at a few fma per 16 bytes).
 // ---------------------------------------------------------------------------------------------
-constexpr int AP_THREADS = 128;
+constexpr int AR_THREADS = 128;   // == OMB_TB: one CTA iteration sweeps one tile
+constexpr int ar_min_blocks(int lmax) { return lmax <= 16 ? 6 : (lmax <= 32 ? 4 : (lmax <= 48 ? 3 : 2)); }
 
-__global__ void __launch_bounds__(AP_THREADS)
-qr_apply_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ld, int64_t n, int L, int t,
-                const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-                int64_t s_total, Cand* __restrict__ cand)
+template <int LMAX>
+__global__ void __launch_bounds__(AR_THREADS, ar_min_blocks(LMAX))
+qr_apply1_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L,
+                 const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
+                 int64_t s_total, Cand* __restrict__ cand)
 {
-    extern __shared__ double sm[];
-    double* s_V = sm;                                   // (t+1) x L
-    double* s_col = sm + (size_t)(t + 1) * L;           // L x AP_THREADS
-    __shared__ double s_tau[QR_BMAX];
-    __shared__ Cand s_c[AP_THREADS / 32];
-    for (int e = threadIdx.x; e < (t + 1) * L; e += AP_THREADS) {
-        const int tt = e / L, k = e - tt * L;
-        s_V[e] = P->V[tt][k];
+    __shared__ double s_v[LMAX];
+    __shared__ double s_tau;
+    __shared__ Cand s_c[AR_THREADS / 32];
+    for (int k = threadIdx.x; k < LMAX; k += AR_THREADS) s_v[k] = (k < L) ? P->V[0][k] : 0.0;
+    if (threadIdx.x == 0) s_tau = P->tau[0];
+    __syncthreads();
+    const double tau = s_tau;
+    const bool last_row = (L == 1);
+
+    Cand best = cand_empty();
+    const int64_t ntiles = basis_tiles(n);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t j = tile * OMB_TB + threadIdx.x;
+        if (j >= n) continue;
+        const double* col = src + tile * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + threadIdx.x;
+        double* outp = dst + tile * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + threadIdx.x;
+        double c[LMAX];
+#pragma unroll
+        for (int k = 0; k < LMAX; ++k) c[k] = (k < L) ? ldg_stream(col + k * OMB_TB) : 0.0;
+        // w = v^T c (v[0] = 1; rows k >= L hold exact zeros)
+        double w = c[0];
+#pragma unroll
+        for (int k = 1; k < LMAX; ++k) w = fma(s_v[k], c[k], w);
+        const double tw = tau * w;
+        const double rij = c[0] - tw;
+#pragma unroll
+        for (int k = 1; k < LMAX; ++k) {
+            c[k] = fma(-tw, s_v[k], c[k]);
+            if (k < L) stg_stream(outp + k * OMB_TB, c[k]);
+        }
+        double v1 = vn1[j];
+        if (v1 >= 0.0) {
+            if (v1 != 0.0) {
+                const double v2 = vn2[j];
+                if (downdate(rij, v1, v2)) {
+                    double sq = 0.0;
+#pragma unroll
+                    for (int k = 1; k < LMAX; ++k) sq = fma(c[k], c[k], sq);
+                    v1 = last_row ? 0.0 : sqrt(sq);
+                    vn2[j] = v1;
+                }
+                vn1[j] = v1;
+            }
+            const int64_t key = j < s_total ? P->posmap[j] : j;
+            cand_push(best, v1, j, key);
+        }
     }
-    if (threadIdx.x <= t) s_tau[threadIdx.x] = P->tau[threadIdx.x];
+    best = cand_block_reduce(best, s_c);
+    if (threadIdx.x == 0) cand[blockIdx.x] = best;
+}
+
+typedef void (*Apply1Fn)(const double*, double*, int64_t, int, int, int, const Panel*, double*, double*, int64_t,
+                         Cand*);
+static Apply1Fn pick_apply1(int L, int* lmax)
+{
+    if (L <= 16) { *lmax = 16; return qr_apply1_kernel<16>; }
+    if (L <= 32) { *lmax = 32; return qr_apply1_kernel<32>; }
+    if (L <= 48) { *lmax = 48; return qr_apply1_kernel<48>; }
+    if (L <= 64) { *lmax = 64; return qr_apply1_kernel<64>; }
+    if (L <= 80) { *lmax = 80; return qr_apply1_kernel<80>; }
+    if (L <= QR_LREG) { *lmax = QR_LREG; return qr_apply1_kernel<QR_LREG>; }
+    return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked apply pass on the FP64 tensor path (up to 8 reflectors per block):
+//     C^T <- C^T - ((C^T V) T) V^T        for groups of 8 candidate columns,
+// i.e. three small GEMMs per group on DMMA.8x8x4.  A warp owns 8*NG columns; each lane keeps
+// C[8G + 2p + e][col] (p = lane%4, e = 0,1, col = lane/4 of its group) -- which is at once the
+// A fragment of the first product (rows taken in the order {0,2,4,6},{1,3,5,7} of each group of
+// eight) and the accumulator fragment of the last one, so nothing is shuffled or staged: every
+// element is read once from HBM and written once.  The reflector fragments come from shared
+// memory once per 8-row group and are reused by the NG column groups (one LDS per 4*NG*256 FMAs;
+// a DFMA formulation needs one operand fetch per FMA and is issue-bound).
+// ---------------------------------------------------------------------------------------------
+constexpr int AM_THREADS = 128;
+constexpr int AM_SV = 10;     // row stride of sV  [row][refl]   : (2p*10 + c) distinct mod 16
+constexpr int AM_ST = 10;     // row stride of sT  [refl][refl']
+
+template <int LG, int NG>
+__global__ void __launch_bounds__(AM_THREADS)
+qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L, int t,
+                    const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
+                    int64_t s_total, Cand* __restrict__ cand)
+{
+    constexpr int LP = LG * 8;                 // padded rows
+    constexpr int SVT = LP + 2;                // row stride of sVt [refl][row]: == 2 (mod 8)
+    constexpr int WT = 8 * NG;                 // columns per warp tile (divides OMB_TB)
+    __shared__ double sV[LP * AM_SV];
+    __shared__ double sVt[8 * SVT];
+    __shared__ double sT[8 * AM_ST];
+    __shared__ Cand s_c[AM_THREADS / 32];
+    for (int e = threadIdx.x; e < LP * 8; e += AM_THREADS) {
+        const int k = e >> 3, a = e & 7;
+        const double v = (k < L && a <= t) ? P->V[a][k] : 0.0;
+        sV[k * AM_SV + a] = v;
+        sVt[a * SVT + k] = v;
+    }
+    if (threadIdx.x < 64) {
+        const int a = threadIdx.x >> 3, b = threadIdx.x & 7;
+        sT[a * AM_ST + b] = (a <= b && b <= t) ? P->T[a][b] : 0.0;
+    }
     __syncthreads();
 
-    Cand best;
-    best.best = -1.0; best.second = -1.0; best.idx = -1; best.key = INT64_MAX;
-    double* c = s_col + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = lane & 3, cq = lane >> 2;
+    const int tG = t >> 3, tp = (t & 7) >> 1, te = t & 1;
     const bool last_row = (t + 1 == L);
 
-    for (int64_t j0 = (int64_t)blockIdx.x * AP_THREADS; j0 < n; j0 += (int64_t)gridDim.x * AP_THREADS) {
-        const int64_t j = j0 + threadIdx.x;
-        if (j < n) {
-            const double* col = src + j;
-            int k = 0;
-            for (; k + 8 <= L; k += 8) {
-                double a[8];
+    Cand best = cand_empty();
+    const int64_t nwt = basis_tiles(n) * (OMB_TB / WT);
+    for (int64_t wt = (int64_t)blockIdx.x * (AM_THREADS / 32) + warp; wt < nwt;
+         wt += (int64_t)gridDim.x * (AM_THREADS / 32)) {
+        const int64_t j0 = wt * WT;
+        if (j0 >= n) continue;
+        const int64_t tbase = (j0 >> 7) * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + (j0 & (OMB_TB - 1));
+        const double* in = src + tbase + (2 * p) * OMB_TB + cq;
+        double* out = dst + tbase + (2 * p) * OMB_TB + cq;
+        double c[LG][NG][2];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a[u] = ldg_stream(col + (int64_t)(k + u) * ld);
+        for (int G = 0; G < LG; ++G)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) c[(k + u) * AP_THREADS] = a[u];
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * G + 2 * p + e;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    c[G][g][e] = (row < L) ? ldg_stream(in + (8 * G + e) * OMB_TB + 8 * g) : 0.0;
             }
-            for (; k < L; ++k) c[k * AP_THREADS] = ldg_stream(col + (int64_t)k * ld);
-
-            for (int tt = 0; tt <= t; ++tt) {
-                const double* v = s_V + tt * L;
-                double w = c[tt * AP_THREADS];
-                for (int kk = tt + 1; kk < L; ++kk) w = fma(v[kk], c[kk * AP_THREADS], w);
-                const double tw = s_tau[tt] * w;
-                c[tt * AP_THREADS] -= tw;
-                for (int kk = tt + 1; kk < L; ++kk) c[kk * AP_THREADS] = fma(-tw, v[kk], c[kk * AP_THREADS]);
+        // Z^T = C^T V
+        double z[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) z[g][0] = z[g][1] = 0.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double bv = sV[(8 * G + 2 * p + e) * AM_SV + cq];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) dmma884(z[g][0], z[g][1], c[G][g][e], bv);
             }
-            double* out = dst + j;
-            for (int kk = t + 1; kk < L; ++kk) stg_stream(out + (int64_t)kk * ld, c[kk * AP_THREADS]);
-
-            double v1 = vn1[j];
-            if (v1 >= 0.0) {
-                if (v1 != 0.0) {
-                    const double v2 = vn2[j];
-                    if (downdate(c[t * AP_THREADS], v1, v2)) {
-                        double s = 0.0;
-                        for (int kk = t + 1; kk < L; ++kk) { const double x = c[kk * AP_THREADS]; s = fma(x, x, s); }
-                        v1 = last_row ? 0.0 : sqrt(s);
-                        vn2[j] = v1;
-                    }
-                    vn1[j] = v1;
+        // Z'^T = Z^T T
+        double zp[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) zp[g][0] = zp[g][1] = 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double bv = sT[(2 * p + e) * AM_ST + cq];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) dmma884(zp[g][0], zp[g][1], z[g][e], bv);
+        }
+        // C^T -= Z'^T V^T
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { zp[g][0] = -zp[g][0]; zp[g][1] = -zp[g][1]; }
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double bv = sVt[(2 * p + e) * SVT + 8 * G + cq];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) dmma884(c[G][g][0], c[G][g][1], zp[g][e], bv);
+            }
+        // rows below the block go back to HBM; R[i, j] = row t
+        double rij[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) rij[g] = 0.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * G + 2 * p + e;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (G == tG && e == te) rij[g] = c[G][g][e];
+                    if (row > t && row < L) stg_stream(out + (8 * G + e) * OMB_TB + 8 * g, c[G][g][e]);
                 }
+            }
+        // down-date: the lanes holding row t (p == tp) own their column's norms
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int64_t j = j0 + 8 * g + cq;
+            const bool owner = (p == tp) && (j < n);
+            double v1 = owner ? vn1[j] : -1.0;
+            bool redo = false;
+            if (owner && v1 > 0.0) {
+                const double v2 = vn2[j];
+                redo = downdate(rij[g], v1, v2);
+            }
+            if (__any_sync(0xFFFFFFFFu, redo)) {
+                // exact trailing norm: each of the column's 4 lanes sums its rows, then combine
+                double sq = 0.0;
+#pragma unroll
+                for (int G = 0; G < LG; ++G)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int row = 8 * G + 2 * p + e;
+                        if (row > t && row < L) sq = fma(c[G][g][e], c[G][g][e], sq);
+                    }
+                sq += __shfl_xor_sync(0xFFFFFFFFu, sq, 1);
+                sq += __shfl_xor_sync(0xFFFFFFFFu, sq, 2);
+                if (redo) {
+                    v1 = last_row ? 0.0 : sqrt(sq);
+                    vn2[j] = v1;
+                }
+            }
+            if (owner && v1 >= 0.0) {
+                vn1[j] = v1;
                 const int64_t key = j < s_total ? P->posmap[j] : j;
                 cand_push(best, v1, j, key);
             }
@@ -283,6 +446,26 @@ qr_apply_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_
     }
     best = cand_block_reduce(best, s_c);
     if (threadIdx.x == 0) cand[blockIdx.x] = best;
+}
+
+typedef void (*ApplyMmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
+                           int64_t, Cand*);
+
+// tensor-path apply kernel for L rows (L <= 256); *ng = column groups per warp
+static ApplyMmaFn pick_apply_mma(int L, int* ng)
+{
+    const int lg = (L + 7) / 8;
+    switch (lg) {
+#define OMB_AM_CASE(LGV, NGV) case LGV: *ng = NGV; return qr_apply_mma_kernel<LGV, NGV>;
+        OMB_AM_CASE(1, 4) OMB_AM_CASE(2, 4) OMB_AM_CASE(3, 4) OMB_AM_CASE(4, 4) OMB_AM_CASE(5, 4) OMB_AM_CASE(6, 4)
+        OMB_AM_CASE(7, 4) OMB_AM_CASE(8, 4) OMB_AM_CASE(9, 2) OMB_AM_CASE(10, 2) OMB_AM_CASE(11, 2)
+        OMB_AM_CASE(12, 2) OMB_AM_CASE(13, 2) OMB_AM_CASE(14, 2) OMB_AM_CASE(15, 2) OMB_AM_CASE(16, 2)
+#undef OMB_AM_CASE
+        default: break;
+    }
+    if (lg <= 24) { *ng = 1; return qr_apply_mma_kernel<24, 1>; }
+    *ng = 1;
+    return qr_apply_mma_kernel<32, 1>;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,25 +488,44 @@ __device__ __forceinline__ double block_sum(double x, double* s_red)
 
 __global__ void __launch_bounds__(PN_THREADS)
 qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand, const double* __restrict__ src,
-                int64_t ld, int L, int i, int t, int seq_norm, int64_t s_total, int64_t index_base,
+                int r, int i0, int L, int i, int t, int seq_norm, int64_t s_total, int64_t index_base,
                 double* __restrict__ vn1, int64_t* __restrict__ piv, double* __restrict__ rdiag,
                 double* __restrict__ gap)
 {
     __shared__ Cand s_c[PN_THREADS / 32];
-    __shared__ double s_x[QR_RMAX];      // pivot column tail over rows i0..
+    __shared__ double s_V[QR_BMAX][QR_RMAX];   // earlier reflectors of this block (rows < t), then v_t
+    __shared__ double s_T[QR_BMAX][QR_BMAX];
+    __shared__ double s_x[QR_RMAX];            // pivot column tail over rows i0..
     __shared__ double s_z[QR_BMAX];
     __shared__ double s_red[PN_THREADS / 32];
     __shared__ int64_t s_p;
-    __shared__ double s_beta, s_tau, s_scal;
+    __shared__ double s_tau, s_scal;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // 0. block state -> shared memory (independent of the pivot: overlaps the argmax reduction)
+    for (int e = threadIdx.x; e < t * L; e += PN_THREADS) {
+        const int a = e / L, k = e - a * L;
+        s_V[a][k] = P->V[a][k];
+    }
+    for (int e = threadIdx.x; e < t * t; e += PN_THREADS) {
+        const int a = e / t, b = e - a * t;
+        s_T[a][b] = P->T[a][b];
+    }
 
     // 1. global argmax over the pass kernel's records
-    Cand c;
-    c.best = -1.0; c.second = -1.0; c.idx = -1; c.key = INT64_MAX;
+    Cand c = cand_empty();
     for (int e = threadIdx.x; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
     c = cand_block_reduce(c, s_c);
+    if (threadIdx.x == 0) s_p = c.idx;
+    __syncthreads();
+    const int64_t p = s_p;
+
+    // 2. pivot column tail at block start (all threads) while thread 0 does LAPACK's bookkeeping
+    {
+        const double* col = src + basis_index(i0, p, r);
+        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = col[(int64_t)k * OMB_TB];
+    }
     if (threadIdx.x == 0) {
-        const int64_t p = c.idx;
-        s_p = p;
         piv[i] = p + index_base;
         gap[i] = (c.second < 0.0 || c.best <= 0.0) ? 1.0 : (c.best - c.second) / c.best;
         // LAPACK's swap of positions i <-> pos(p): the column sitting at position i moves to pos(p)
@@ -338,35 +540,27 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         vn1[p] = -1.0;                   // never a candidate again
     }
     __syncthreads();
-    const int64_t p = s_p;
-
-    // 2. pivot column tail at block start, then the block's earlier reflectors (compact WY)
-    for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = src[(int64_t)k * ld + p];
-    __syncthreads();
     if (t > 0) {
-        // z = V^T x  (one warp per reflector), z' = T^T z, x -= V z'
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // x <- Q^T x = x - V (T^T (V^T x))   (compact WY of the block's earlier reflectors)
         for (int tt = warp; tt < t; tt += PN_THREADS / 32) {
-            double s = 0.0;
-            for (int k = lane; k < L; k += 32) s = fma(P->V[tt][k], s_x[k], s);
+            double sacc = 0.0;
+            for (int k = lane; k < L; k += 32) sacc = fma(s_V[tt][k], s_x[k], sacc);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-            if (lane == 0) s_z[tt] = s;
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, o);
+            if (lane == 0) s_z[tt] = sacc;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double zz[QR_BMAX];
-            for (int a = 0; a < t; ++a) {
-                double s = 0.0;
-                for (int b = 0; b <= a; ++b) s = fma(P->T[b][a], s_z[b], s);   // (T^T z)_a
-                zz[a] = s;
-            }
-            for (int a = 0; a < t; ++a) s_z[a] = zz[a];
+        double zz = 0.0;
+        if (threadIdx.x < t) {
+            const int a = threadIdx.x;
+            for (int b = 0; b <= a; ++b) zz = fma(s_T[b][a], s_z[b], zz);      // (T^T z)_a
         }
+        __syncthreads();
+        if (threadIdx.x < t) s_z[threadIdx.x] = zz;
         __syncthreads();
         for (int k = threadIdx.x; k < L; k += PN_THREADS) {
             double x = s_x[k];
-            for (int a = 0; a < t; ++a) x = fma(-P->V[a][k], s_z[a], x);
+            for (int a = 0; a < t; ++a) x = fma(-s_V[a][k], s_z[a], x);
             s_x[k] = x;
         }
         __syncthreads();
@@ -376,17 +570,17 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
     double xn2;
     if (seq_norm) {
         if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int k = t + 1; k < L; ++k) s = fma(s_x[k], s_x[k], s);
-            s_red[0] = s;
+            double sacc = 0.0;
+            for (int k = t + 1; k < L; ++k) sacc = fma(s_x[k], s_x[k], sacc);
+            s_red[0] = sacc;
         }
         __syncthreads();
         xn2 = s_red[0];
         __syncthreads();
     } else {
-        double s = 0.0;
-        for (int k = t + 1 + threadIdx.x; k < L; k += PN_THREADS) s = fma(s_x[k], s_x[k], s);
-        xn2 = block_sum(s, s_red);
+        double sacc = 0.0;
+        for (int k = t + 1 + threadIdx.x; k < L; k += PN_THREADS) sacc = fma(s_x[k], s_x[k], sacc);
+        xn2 = block_sum(sacc, s_red);
     }
     if (threadIdx.x == 0) {
         const double alpha = s_x[t];
@@ -402,7 +596,7 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
             tau = (beta - alpha) / beta;
             scal = 1.0 / (alpha - beta);
         }
-        s_beta = beta; s_tau = tau; s_scal = scal;
+        s_tau = tau; s_scal = scal;
         rdiag[i] = beta;
         P->tau[t] = tau;
     }
@@ -413,45 +607,45 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         if (k == t) v = 1.0;
         else if (k > t) v = (tau != 0.0) ? s_x[k] * scal : 0.0;
         P->V[t][k] = v;
-        s_x[k] = v;                      // s_x now holds v_t
+        s_V[t][k] = v;
     }
     __syncthreads();
 
-    // 4. compact WY column t of T and q = Q e_t = e_t - V T (V^T e_t)   (blocked runs only use q)
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int tt = warp; tt < t; tt += PN_THREADS / 32) {
-            double s = 0.0;
-            for (int k = lane; k < L; k += 32) s = fma(P->V[tt][k], s_x[k], s);     // V[:, tt]^T v_t
+    // 4. compact-WY column t of T, and q = Q e_t = e_t - V T (V^T e_t)
+    for (int tt = warp; tt < t; tt += PN_THREADS / 32) {
+        double sacc = 0.0;
+        for (int k = lane; k < L; k += 32) sacc = fma(s_V[tt][k], s_V[t][k], sacc);     // V[:, tt]^T v_t
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-            if (lane == 0) s_z[tt] = s;
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, o);
+        if (lane == 0) s_z[tt] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x <= t) {
+        // T[0:t, t] = -tau * T[0:t, 0:t] * (V^T v_t);  T[t][t] = tau
+        const int a = threadIdx.x;
+        double val = tau;
+        if (a < t) {
+            double sacc = 0.0;
+            for (int b = a; b < t; ++b) sacc = fma(s_T[a][b], s_z[b], sacc);
+            val = -tau * sacc;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // T[0:t, t] = -tau * T[0:t, 0:t] * s_z ; T[t][t] = tau
-            double col[QR_BMAX];
-            for (int a = 0; a < t; ++a) {
-                double s = 0.0;
-                for (int b = a; b < t; ++b) s = fma(P->T[a][b], s_z[b], s);
-                col[a] = -tau * s;
-            }
-            for (int a = 0; a < t; ++a) P->T[a][t] = col[a];
-            P->T[t][t] = tau;
-            // g = T * (V^T e_t) with (V^T e_t)_a = V[a][t]  (a <= t)
-            for (int a = 0; a <= t; ++a) {
-                double s = 0.0;
-                for (int b = a; b <= t; ++b) s = fma(P->T[a][b], (b == t) ? 1.0 : P->V[b][t], s);
-                s_z[a] = s;
-            }
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < L; k += PN_THREADS) {
-            double qv = (k == t) ? 1.0 : 0.0;
-            for (int a = 0; a < t; ++a) qv = fma(-P->V[a][k], s_z[a], qv);
-            qv = fma(-s_x[k], s_z[t], qv);
-            P->q[k] = qv;
-        }
+        s_T[a][t] = val;
+        P->T[a][t] = val;
+    }
+    __syncthreads();
+    double g = 0.0;
+    if (threadIdx.x <= t) {
+        // g = T * (V^T e_t),  (V^T e_t)_b = V[b][t]
+        const int a = threadIdx.x;
+        for (int b = a; b <= t; ++b) g = fma(s_T[a][b], s_V[b][t], g);
+    }
+    __syncthreads();
+    if (threadIdx.x <= t) s_z[threadIdx.x] = g;
+    __syncthreads();
+    for (int k = threadIdx.x; k < L; k += PN_THREADS) {
+        double qv = (k == t) ? 1.0 : 0.0;
+        for (int a = 0; a <= t; ++a) qv = fma(-s_V[a][k], s_z[a], qv);
+        P->q[k] = qv;
     }
 }
 
@@ -466,12 +660,13 @@ struct QrWs {
 static int64_t qr_ws_layout(int64_t n, QrWs* w, char* base)
 {
     int64_t off = 0;
+    const int64_t npad = basis_tiles(n) * OMB_TB;
     auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return base ? base + o : (char*)nullptr; };
-    char* a = take((int64_t)sizeof(double) * (n + 2));
-    char* b = take((int64_t)sizeof(double) * (n + 2));
+    char* a = take((int64_t)sizeof(double) * npad);
+    char* b = take((int64_t)sizeof(double) * npad);
     char* c = take((int64_t)sizeof(Cand) * QR_NCAND);
     char* d = take((int64_t)sizeof(Panel));
-    char* e = take((int64_t)sizeof(double) * (n + 2));
+    char* e = take((int64_t)sizeof(double) * npad);
     if (w) { w->vn1 = (double*)a; w->vn2 = (double*)b; w->cand = (Cand*)c; w->panel = (Panel*)d; w->vn_tmp = (double*)e; }
     return off;
 }
@@ -487,28 +682,28 @@ extern "C" int64_t omb_qrcp_ws_bytes(int64_t n, int64_t r)
     return qr_ws_layout(n, nullptr, nullptr);
 }
 
-extern "C" int omb_qrcp(const double* d_Ut, int64_t ld, int64_t n, int64_t r, int64_t s, const double* d_vn,
-                        double* d_work, void* d_ws, int block, int64_t index_base, int64_t* d_piv,
-                        double* d_rdiag, double* d_gap, void* stream)
+extern "C" int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
+                        void* d_ws, int block, int64_t index_base, int64_t* d_piv, double* d_rdiag, double* d_gap,
+                        void* stream)
 {
     OMB_CHECK_ARG(d_Ut && d_work && d_ws && d_piv && d_rdiag && d_gap, "null pointer");
     OMB_CHECK_ARG(n > 0 && r > 0 && s > 0, "non-positive size");
     OMB_CHECK_ARG(r <= QR_RMAX, "r exceeds the supported number of modes (256)");
     OMB_CHECK_ARG(s <= r && s <= n, "s must be <= min(r, n)");
-    OMB_CHECK_ARG(ld >= n && (ld % 2) == 0, "ld must be even and >= n");
-    OMB_CHECK_ARG(block >= 1 && block <= QR_BMAX, "block must be in [1, 16]");
+    OMB_CHECK_ARG(block >= 1 && block <= QR_BMAX, "block must be in [1, 8]");
     OMB_CHECK_ARG((((uintptr_t)d_Ut | (uintptr_t)d_work) & 15) == 0, "basis pointers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     QrWs w;
     qr_ws_layout(n, &w, (char*)d_ws);
     const int sms = sm_count();
+    const int ri = (int)r;
     int rc;
 
     const double* vn = d_vn;
     if (!vn) {
         int64_t g = ceil_div(n, 256);
         if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
-        qr_norms_kernel<<<(unsigned)g, 256, 0, st>>>(d_Ut, ld, n, (int)r, w.vn_tmp);
+        qr_norms_kernel<<<(unsigned)g, 256, 0, st>>>(d_Ut, n, ri, w.vn_tmp);
         if ((rc = check_launch("qr_norms_kernel"))) return rc;
         vn = w.vn_tmp;
     }
@@ -519,49 +714,51 @@ extern "C" int omb_qrcp(const double* d_Ut, int64_t ld, int64_t n, int64_t r, in
         if ((rc = check_launch("qr_init_kernel"))) return rc;
     }
 
-    int64_t gv_grid = ceil_div((n + 1) / 2, GV_THREADS);
+    const int64_t ntiles = basis_tiles(n);
+    int64_t gv_grid = ceil_div(ntiles * (OMB_TB / 2), GV_THREADS);
     if (gv_grid > (int64_t)sms * 8) gv_grid = (int64_t)sms * 8;
     if (gv_grid > QR_NCAND) gv_grid = QR_NCAND;
 
     // step-0 argmax: a read-only pass over zero rows leaves the norms untouched
-    qr_gemv_kernel<<<(unsigned)gv_grid, GV_THREADS, 0, st>>>(d_Ut, ld, n, 0, 0, 0, w.panel, w.vn1, w.vn2, s, w.cand);
+    qr_gemv_kernel<<<(unsigned)gv_grid, GV_THREADS, 0, st>>>(d_Ut, n, ri, 0, 0, 0, 0, w.panel, w.vn1, w.vn2, s, w.cand);
     if ((rc = check_launch("qr_gemv_kernel"))) return rc;
     int ncand = (int)gv_grid;
 
     const double* src = d_Ut;   // trailing matrix as of the block start, rows i0..r-1
     int i0 = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        OMB_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        const int L = (int)r - i0;
-        qr_panel_kernel<<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, ncand, src + (int64_t)i0 * ld, ld, L, i, t,
-                                                   block == 1 ? 1 : 0, s, index_base, w.vn1, d_piv, d_rdiag, d_gap);
+        const int L = ri - i0;
+        qr_panel_kernel<<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, ncand, src, ri, i0, L, i, t, block == 1 ? 1 : 0, s,
+                                                   index_base, w.vn1, d_piv, d_rdiag, d_gap);
         if ((rc = check_launch("qr_panel_kernel"))) return rc;
         if (i == (int)s - 1) break;           // no further pivot needed: skip the last pass
-        const bool close_block = (t == block - 1);
-        if (close_block) {
-            const size_t smem = sizeof(double) * ((size_t)(t + 1) * L + (size_t)L * AP_THREADS);
-            OMB_CHECK_ARG(smem <= 220 * 1024, "trailing block too tall for the apply kernel");
-            int per_sm = (int)((220 * 1024) / (smem + 1024));
-            if (per_sm < 1) per_sm = 1;
-            if (per_sm > 8) per_sm = 8;
-            int64_t g = ceil_div(n, AP_THREADS);
-            if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
-            if (g > QR_NCAND) g = QR_NCAND;
-            qr_apply_kernel<<<(unsigned)g, AP_THREADS, smem, st>>>(src + (int64_t)i0 * ld, d_work + (int64_t)i0 * ld,
-                                                                   ld, n, L, t, w.panel, w.vn1, w.vn2, s, w.cand);
-            if ((rc = check_launch("qr_apply_kernel"))) return rc;
+        if (t == block - 1) {
+            int64_t g;
+            int lmax = 0, ng = 0;
+            Apply1Fn f1 = (block == 1) ? pick_apply1(L, &lmax) : nullptr;
+            if (f1) {
+                g = ntiles;
+                if (g > (int64_t)sms * ar_min_blocks(lmax)) g = (int64_t)sms * ar_min_blocks(lmax);   // one wave
+                if (g > QR_NCAND) g = QR_NCAND;
+                f1<<<(unsigned)g, AR_THREADS, 0, st>>>(src, d_work, n, ri, i0, L, w.panel, w.vn1, w.vn2, s, w.cand);
+                if ((rc = check_launch("qr_apply1_kernel"))) return rc;
+            } else {
+                // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
+                //  tensor-path rounding instead of the oracle's fma order)
+                ApplyMmaFn fm = pick_apply_mma(L, &ng);
+                g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
+                if (g > (int64_t)sms * 3) g = (int64_t)sms * 3;
+                if (g > QR_NCAND) g = QR_NCAND;
+                fm<<<(unsigned)g, AM_THREADS, 0, st>>>(src, d_work, n, ri, i0, L, t, w.panel, w.vn1, w.vn2, s, w.cand);
+                if ((rc = check_launch("qr_apply_mma_kernel"))) return rc;
+            }
             ncand = (int)g;
             src = d_work;
             i0 = i + 1;
         } else {
-            qr_gemv_kernel<<<(unsigned)gv_grid, GV_THREADS, 0, st>>>(src + (int64_t)i0 * ld, ld, n, L, t,
-                                                                    (t + 1 == L) ? 1 : 0, w.panel, w.vn1, w.vn2, s,
-                                                                    w.cand);
+            qr_gemv_kernel<<<(unsigned)gv_grid, GV_THREADS, 0, st>>>(src, n, ri, i0, L, t, (t + 1 == L) ? 1 : 0, w.panel,
+                                                                    w.vn1, w.vn2, s, w.cand);
             if ((rc = check_launch("qr_gemv_kernel"))) return rc;
             ncand = (int)gv_grid;
         }

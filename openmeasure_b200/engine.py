@@ -8,8 +8,8 @@ Data layout in HBM (FP64 throughout):
     X      (F * n_c_loc, m) C-order snapshot shard, feature-major, exactly the reference's layout
     cnt    (F * n_c_loc,)   centring value per row          (reference X_cnt[:, 0])
     scl    (F,)             scale per feature block         (reference X_scl[f * n_points, 0])
-    Ut     (r, ld)          mode-major basis, Ut[q, i] = U_r[i, q]; ld = n_loc rounded up to 16
-    work   (r, ld)          trailing matrix of the pivoted QR
+    Ut     (ntiles, r, 128) tiled mode-major basis, Ut[i // 128, q, i % 128] = U_r[i, q]
+    work   (ntiles, r, 128) trailing matrix of the pivoted QR
 With torch.distributed initialised, every rank holds the cells [c0, c0 + n_c_loc) of EVERY
 feature; only F*4 statistics, the m x m Gram and (per pivot step) one small record cross NVLink.
 """
@@ -44,8 +44,11 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def ld_for(n):
-    return (int(n) + 15) // 16 * 16
+TB = 128    # candidates per basis tile (OMB_TB in csrc/common.cuh)
+
+
+def tiles_for(n):
+    return (int(n) + TB - 1) // TB
 
 
 class Engine:
@@ -84,7 +87,7 @@ class Engine:
         self.Ut = None
         self.vn = None
         self.r = None
-        self.ld = ld_for(self.n_loc)
+        self.ntiles = tiles_for(self.n_loc)
         self.timings = {}
 
     # ------------------------------------------------------------------------------------ K1
@@ -176,12 +179,18 @@ class Engine:
         W = W.contiguous()
         m, r = (int(v) for v in W.shape)
         assert m == self.m
-        Ut = torch.zeros(r, self.ld, dtype=torch.float64, device=self.dev)
-        vn = torch.zeros(self.ld, dtype=torch.float64, device=self.dev) if norms else None
+        Ut = self._new_basis(r)
+        vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev) if norms else None
         _lib.call("omb_backproject", _p(self.X), self.F, self.n_c_loc, self.m,
                   _p(self.cnt if centred else None), _p(self.scl if scaled else None), _p(W), r,
-                  _p(Ut), self.ld, _p(vn), _stream())
+                  _p(Ut), _p(vn), _stream())
         self.Ut, self.vn, self.r = Ut, vn, r
+        return Ut
+
+    def _new_basis(self, r):
+        Ut = torch.empty(self.ntiles, r, TB, dtype=torch.float64, device=self.dev)
+        if self.n_loc % TB:
+            Ut[-1].zero_()           # padding candidates of the last tile
         return Ut
 
     def set_basis_rows(self, Ur_dev):
@@ -189,22 +198,22 @@ class Engine:
         Ur_dev = Ur_dev.contiguous()
         n, r = (int(v) for v in Ur_dev.shape)
         assert n == self.n_loc
-        Ut = torch.zeros(r, self.ld, dtype=torch.float64, device=self.dev)
-        vn = torch.zeros(self.ld, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_rows_to_modes", _p(Ur_dev), n, r, _p(Ut), self.ld, _p(vn), _stream())
+        Ut = self._new_basis(r)
+        vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_rows_to_modes", _p(Ur_dev), n, r, _p(Ut), _p(vn), _stream())
         self.Ut, self.vn, self.r = Ut, vn, r
 
     def basis_rows(self):
         """(n_loc, r) C-order copy of the basis on device."""
         out = torch.empty(self.n_loc, self.r, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_modes_to_rows", _p(self.Ut), self.ld, self.n_loc, self.r, _p(out), _stream())
+        _lib.call("omb_modes_to_rows", _p(self.Ut), self.n_loc, self.r, _p(out), _stream())
         return out
 
     def mask_rows(self, mask_dev):
         """optimal_placement(mask=...): zero the excluded rows of the basis in place (:737-738)."""
-        keep = torch.zeros(self.ld, dtype=torch.bool, device=self.dev)
-        keep[: self.n_loc] = mask_dev
-        self.Ut[:, : self.n_loc].mul_(keep[: self.n_loc].to(torch.float64))
+        keep = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev)
+        keep[: self.n_loc] = mask_dev.to(torch.float64)
+        self.Ut.mul_(keep.view(self.ntiles, 1, TB))
         self.vn = None      # recomputed by the placement
 
     # ------------------------------------------------------------------------------------ K6
@@ -214,12 +223,13 @@ class Engine:
             raise NotImplementedError("multi-rank placement is driven by openmeasure_b200.parallel")
         r = self.r
         s = r if s is None else int(s)
-        work = torch.empty(r, self.ld, dtype=torch.float64, device=self.dev)
+        block = max(1, min(8, int(block)))
+        work = torch.empty(self.ntiles, r, TB, dtype=torch.float64, device=self.dev)
         ws = _ws(_lib.load().omb_qrcp_ws_bytes(self.n_loc, r), self.dev)
         piv = torch.empty(s, dtype=torch.int64, device=self.dev)
         rdiag = torch.empty(s, dtype=torch.float64, device=self.dev)
         gap = torch.empty(s, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_qrcp", _p(self.Ut), self.ld, self.n_loc, r, s, _p(self.vn), _p(work), _p(ws),
+        _lib.call("omb_qrcp", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(work), _p(ws),
                   int(block), 0, _p(piv), _p(rdiag), _p(gap), _stream())
         return piv, rdiag, gap
 
@@ -228,7 +238,7 @@ class Engine:
         s = int(piv_dev.numel())
         Theta = torch.empty(s, self.r, dtype=torch.float64, device=self.dev)
         cnt_s = torch.empty(s, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_gather_rows", _p(self.Ut), self.ld, self.r, _p(piv_dev), s, _p(Theta),
+        _lib.call("omb_gather_rows", _p(self.Ut), self.r, _p(piv_dev), s, _p(Theta),
                   _p(self.cnt), _p(cnt_s), _stream())
         return Theta, cnt_s
 
@@ -248,7 +258,7 @@ class Engine:
         nrows = self.n_loc - row0 if nrows is None else int(nrows)
         if out is None:
             out = torch.empty(nrows, N, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_reconstruct", _p(self.Ut), self.ld, r, _p(A_dev), N, _p(self.cnt), _p(self.scl),
+        _lib.call("omb_reconstruct", _p(self.Ut), self.n_loc, r, _p(A_dev), N, _p(self.cnt), _p(self.scl),
                   self.n_c_loc, int(row0), nrows, _p(out), _stream())
         return out
 

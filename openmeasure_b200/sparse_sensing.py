@@ -252,21 +252,30 @@ class ROM:
     def _pod(self, eng, select_modes, n_modes, centred, scaled):
         G = eng.gram(centred=centred, scaled=scaled)
         S, V = eng.eig_pod(G)
-        S_h = S.cpu().numpy()
-        lam = S_h ** 2
-        exp_variance = 100 * np.cumsum(lam) / np.sum(lam)     # :274-275
-        r = self._choose_rank(exp_variance, eng.m, select_modes, n_modes)
+        S_h = None
+        if select_modes == 'number':                          # r known: no host round trip yet
+            r = self._choose_rank(None, eng.m, select_modes, n_modes)
+        else:
+            S_h = S.cpu().numpy()
+            lam = S_h ** 2
+            r = self._choose_rank(100 * np.cumsum(lam) / np.sum(lam), eng.m, select_modes, n_modes)
         Sr = S[:r]
         # modes whose singular value is numerically zero carry no information (row-centred data
         # has rank m-1): back-project them with a zero weight instead of dividing by ~0
         safe = Sr > S[0] * (eng.m * _eng.EPS)
         W = torch.where(safe, 1.0 / torch.where(safe, Sr, torch.ones_like(Sr)), torch.zeros_like(Sr))
         eng.backproject((V[:, :r] * W).contiguous(), centred=centred, scaled=scaled)
-        Ar = (V[:, :r] * Sr).cpu().numpy()                    # A = V Sigma (:273)
+        Ar_d = V[:, :r] * Sr                                  # A = V Sigma (:273)
+        if S_h is None:
+            S_h = S.cpu().numpy()
+        lam = S_h ** 2
+        exp_variance = 100 * np.cumsum(lam) / np.sum(lam)     # :274-275
+        Ar = Ar_d.cpu().numpy()
         self.r = r
         self._host.pop("Ur", None)
         self.pod_sigma = S_h
-        self.pod_rel_err_bound = float(_eng.EPS * (S_h[0] / max(S_h[r - 1], 1e-300)) ** 2)
+        with np.errstate(over="ignore", divide="ignore"):
+            self.pod_rel_err_bound = float(_eng.EPS * (S_h[0] / max(S_h[r - 1], 1e-300)) ** 2)
         return Ar, exp_variance[:r]
 
     def decomposition(self, X0, select_modes='variance', n_modes=99):
