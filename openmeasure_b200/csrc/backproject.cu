@@ -136,6 +136,119 @@ static int launch_bp(const double* X, int64_t n, int64_t n_c, int m, const doubl
     return check_launch("backproject_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few-snapshot variant (m <= 64, r <= 64): one CTA = one basis tile of 128 rows, 8 warps x 16 rows.
+// The A fragments (X - cnt, 8 rows x 4 snapshots = eight 32-byte sectors per load) are read
+// straight from global memory -- a row's 8m bytes stay in L1 across its ceil(m/4) k-steps -- so X
+// makes exactly one trip from HBM and there is no shared-memory staging or barrier in the main
+// loop.  W is staged once per CTA.  The 128 x r result tile is assembled in shared memory in the
+// tile's own layout [q][128] and leaves with ONE bulk (TMA) store of r KB; the dgeqp3 norms are
+// summed from the same tile, sequentially over the modes.
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_THREADS2 = 256;
+
+template <int QB>
+__global__ void __launch_bounds__(BS_THREADS2)
+backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, const double* __restrict__ cnt,
+                         const double* __restrict__ scl, const double* __restrict__ W, int r,
+                         double* __restrict__ Ut, double* __restrict__ vn)
+{
+    constexpr int QC = QB * 8;
+    constexpr int LDW = QC + 4;                    // == 4 (mod 16)
+    extern __shared__ __align__(128) double smem[];
+    double* sC = smem;                             // [r][128]   (tile layout, bulk-stored)
+    double* sW = smem + 64 * OMB_TB;               // [mp][LDW]
+    const int mp = (m + 3) & ~3;
+    for (int e = threadIdx.x; e < mp * QC; e += BS_THREADS2) {
+        const int k = e / QC, q = e - k * QC;
+        sW[k * LDW + q] = (k < m && q < r) ? W[(int64_t)k * r + q] : 0.0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane & 3, fc = lane >> 2;
+    const int64_t ntiles = basis_tiles(n);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t rowb = tile * OMB_TB + warp * 16;
+        const int64_t r0 = rowb + fc, r1 = rowb + 8 + fc;
+        const bool ok0 = r0 < n, ok1 = r1 < n;
+        const double c0 = (ok0 && cnt) ? cnt[r0] : 0.0, c1 = (ok1 && cnt) ? cnt[r1] : 0.0;
+        const double s0 = (ok0 && scl) ? scl[r0 / n_c] : 1.0, s1 = (ok1 && scl) ? scl[r1 / n_c] : 1.0;
+        const double* x0 = X + r0 * m + fr;
+        const double* x1 = X + r1 * m + fr;
+        double acc[2][QB][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < QB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        constexpr int KU = 6;      // k-steps whose loads are issued together (bytes in flight)
+#pragma unroll 1
+        for (int kc = 0; kc < mp; kc += 4 * KU) {
+            double a0[KU], a1[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int k0 = kc + 4 * u;
+                const bool kin = (k0 + fr) < m;
+                a0[u] = (ok0 && kin) ? x0[k0] - c0 : 0.0;
+                a1[u] = (ok1 && kin) ? x1[k0] - c1 : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int k0 = kc + 4 * u;
+                if (k0 < mp) {
+#pragma unroll
+                    for (int b = 0; b < QB; ++b) {
+                        const double bv = sW[(k0 + fr) * LDW + b * 8 + fc];
+                        dmma884(acc[0][b][0], acc[0][b][1], a0[u], bv);
+                        dmma884(acc[1][b][0], acc[1][b][1], a1[u], bv);
+                    }
+                }
+            }
+        }
+        // the previous tile's bulk store must have finished reading sC before it is overwritten
+        if (threadIdx.x == 0) tma_store_wait_read();
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < QB; ++b) {
+            const int q = b * 8 + 2 * fr;
+            if (q < r) {
+                sC[q * OMB_TB + warp * 16 + fc] = acc[0][b][0] / s0;
+                sC[q * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][0] / s1;
+            }
+            if (q + 1 < r) {
+                sC[(q + 1) * OMB_TB + warp * 16 + fc] = acc[0][b][1] / s0;
+                sC[(q + 1) * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][1] / s1;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_store_bulk(Ut + tile * ((int64_t)r * OMB_TB), sC, (uint32_t)(r * OMB_TB * sizeof(double)));
+            tma_store_commit();
+        }
+        if (vn && threadIdx.x < OMB_TB) {
+            double nrm = 0.0;
+            for (int q = 0; q < r; ++q) { const double u = sC[q * OMB_TB + threadIdx.x]; nrm = fma(u, u, nrm); }
+            vn[tile * OMB_TB + threadIdx.x] = sqrt(nrm);
+        }
+    }
+    if (threadIdx.x == 0) tma_store_wait_read();
+}
+
+template <int QB>
+static int launch_bp_small(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl,
+                           const double* W, int r, double* Ut, double* vn, cudaStream_t st)
+{
+    const int mp = (m + 3) & ~3;
+    const size_t bytes = sizeof(double) * (64 * OMB_TB + (size_t)mp * (QB * 8 + 4));
+    OMB_CUDA(cudaFuncSetAttribute(backproject_small_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int64_t grid = basis_tiles(n);
+    int64_t cap = (int64_t)sm_count() * 2;
+    if (grid > cap) grid = cap;
+    backproject_small_kernel<QB><<<(unsigned)grid, BS_THREADS2, bytes, st>>>(X, n, n_c, m, cnt, scl, W, r, Ut, vn);
+    return check_launch("backproject_small_kernel");
+}
+
 }  // namespace omb
 
 using namespace omb;
@@ -149,6 +262,15 @@ extern "C" int omb_backproject(const double* d_X, int64_t F, int64_t n_c, int64_
     const int64_t n = F * n_c;
     OMB_CHECK_ARG(m <= (1 << 20) && r <= (1 << 20), "m or r too large");
     cudaStream_t st = (cudaStream_t)stream;
+    if (m <= 64 && r <= 64) {
+        const int qb = (int)((r + 7) / 8);
+        switch (qb) {
+#define OMB_BPS(QBV) case QBV: return launch_bp_small<QBV>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
+            OMB_BPS(1) OMB_BPS(2) OMB_BPS(3) OMB_BPS(4) OMB_BPS(5) OMB_BPS(6) OMB_BPS(7) OMB_BPS(8)
+#undef OMB_BPS
+            default: break;
+        }
+    }
     if (r <= 64) return launch_bp<8>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
     return launch_bp<16>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
 }

@@ -127,6 +127,114 @@ gram_tile_kernel(const double* __restrict__ X, int64_t n_c, int m, const double*
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few-snapshot variant (m <= 64): the whole m x m Gram fits one warp's accumulators, so every
+// warp sweeps its own rows and keeps the NB(NB+1)/2 upper-triangular 8 x 8 blocks (NB = ceil(m/8))
+// in registers.  A fragment X[k0 + lane%4][8b + lane/4] serves as both operands of the symmetric
+// product, and is loaded straight from global memory (four 64-byte row segments per load; a row's
+// 8m bytes stay in L1 across its NB loads): X makes one trip from HBM, no staging, no barriers.
+// Warps are combined in a fixed order through shared memory; the CTA's partial goes out in the
+// 64 x 64 tile format of the general kernel and is reduced by the same fixed-order pass.
+// ---------------------------------------------------------------------------------------------
+constexpr int GS_THREADS = 256;
+
+template <int NB>
+__global__ void __launch_bounds__(GS_THREADS)
+gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double* __restrict__ cnt,
+                  int64_t rows_per_split, int splits, double* __restrict__ part)
+{
+    __shared__ double s_acc[GT * GT];
+    const int split = blockIdx.x, f = blockIdx.y;
+    const int64_t row_lo = (int64_t)split * rows_per_split;
+    int64_t row_hi = row_lo + rows_per_split;
+    if (row_hi > n_c) row_hi = n_c;
+    const double* Xf = X + (int64_t)f * n_c * m;
+    const double* cf = cnt ? cnt + (int64_t)f * n_c : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane & 3, fc = lane >> 2;
+    constexpr int NW = GS_THREADS / 32;
+
+    double c[NB][NB][2];
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+
+    bool colok[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) colok[b] = (8 * b + fc) < m;
+
+    // warp w takes the k-steps w, w + NW, ... of the CTA's row range (4 rows per step), two at a time
+    for (int64_t k0 = row_lo + 4 * warp; k0 < row_hi; k0 += 8 * NW) {
+        double a[2][NB];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t row = k0 + 4 * NW * u + fr;
+            const bool rok = row < row_hi;
+            const double cv = (rok && cf) ? cf[row] : 0.0;
+            const double* xr = Xf + row * m + fc;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) a[u][b] = (rok && colok[b]) ? xr[8 * b] - cv : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                for (int bj = bi; bj < NB; ++bj) dmma884(c[bi][bj][0], c[bi][bj][1], a[u][bi], a[u][bj]);
+    }
+
+    // fixed-order combination of the warps
+    for (int e = threadIdx.x; e < GT * GT; e += GS_THREADS) s_acc[e] = 0.0;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                for (int bj = bi; bj < NB; ++bj) {
+                    const int i = bi * 8 + fc, j = bj * 8 + 2 * fr;
+                    s_acc[i * GT + j] += c[bi][bj][0];
+                    s_acc[i * GT + j + 1] += c[bi][bj][1];
+                }
+        }
+        __syncthreads();
+    }
+    double* out = part + ((int64_t)f * splits + split) * (GT * GT);
+    for (int e = threadIdx.x; e < GT * GT; e += GS_THREADS) out[e] = s_acc[e];
+}
+
+typedef void (*GramSmallFn)(const double*, int64_t, int, const double*, int64_t, int, double*);
+static GramSmallFn pick_gram_small(int m)
+{
+    switch ((m + 7) / 8) {
+        case 1: return gram_small_kernel<1>;
+        case 2: return gram_small_kernel<2>;
+        case 3: return gram_small_kernel<3>;
+        case 4: return gram_small_kernel<4>;
+        case 5: return gram_small_kernel<5>;
+        case 6: return gram_small_kernel<6>;
+        case 7: return gram_small_kernel<7>;
+        case 8: return gram_small_kernel<8>;
+        default: return nullptr;
+    }
+}
+
+static GramPlan gram_small_plan(int64_t F, int64_t n_c)
+{
+    GramPlan p;
+    p.T = 1;
+    p.ntiles = 1;
+    int64_t splits = ceil_div((int64_t)sm_count() * 2, F);
+    const int64_t unit = 8 * (GS_THREADS / 32);                 // rows per CTA round
+    int64_t max_splits = ceil_div(n_c, 4 * unit);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.rows_per_split = round_up(ceil_div(n_c, splits), unit);
+    p.splits = (int)ceil_div(n_c, p.rows_per_split);
+    return p;
+}
+
 // Gf[f][i][j] = sum over splits (fixed order) of the tile holding (min-tile, max-tile); mirrored.
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const double* __restrict__ part, int m, int T, int ntiles, int splits,
@@ -170,7 +278,7 @@ using namespace omb;
 extern "C" int64_t omb_gram_ws_bytes(int64_t F, int64_t n_c, int64_t m)
 {
     if (F <= 0 || n_c <= 0 || m <= 0) return 0;
-    GramPlan p = gram_plan(F, n_c, m);
+    GramPlan p = (m <= 64) ? gram_small_plan(F, n_c) : gram_plan(F, n_c, m);
     return (int64_t)sizeof(double) * F * p.splits * p.ntiles * GT * GT;
 }
 
@@ -180,12 +288,22 @@ extern "C" int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, co
     OMB_CHECK_ARG(d_X && d_Gf && d_ws, "null pointer");
     OMB_CHECK_ARG(F > 0 && n_c > 0 && m > 0, "non-positive size");
     OMB_CHECK_ARG(F <= 65535 && m <= 16384, "F or m too large");
-    GramPlan p = gram_plan(F, n_c, m);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)p.ntiles, (unsigned)p.splits, (unsigned)F);
-    gram_tile_kernel<<<grid, G_THREADS, 0, st>>>(d_X, n_c, (int)m, d_cnt, p.T, p.rows_per_split, p.splits,
-                                                  (double*)d_ws);
-    int rc = check_launch("gram_tile_kernel");
+    GramPlan p;
+    int rc;
+    if (m <= 64) {
+        p = gram_small_plan(F, n_c);
+        dim3 grid((unsigned)p.splits, (unsigned)F);
+        pick_gram_small((int)m)<<<grid, GS_THREADS, 0, st>>>(d_X, n_c, (int)m, d_cnt, p.rows_per_split, p.splits,
+                                                             (double*)d_ws);
+        rc = check_launch("gram_small_kernel");
+    } else {
+        p = gram_plan(F, n_c, m);
+        dim3 grid((unsigned)p.ntiles, (unsigned)p.splits, (unsigned)F);
+        gram_tile_kernel<<<grid, G_THREADS, 0, st>>>(d_X, n_c, (int)m, d_cnt, p.T, p.rows_per_split, p.splits,
+                                                      (double*)d_ws);
+        rc = check_launch("gram_tile_kernel");
+    }
     if (rc) return rc;
     int64_t gx = ceil_div(m * m, 256);
     if (gx > 2048) gx = 2048;

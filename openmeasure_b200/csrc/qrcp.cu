@@ -183,6 +183,9 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, 
         if (j >= n) continue;
         double y0 = 0.0, y1 = 0.0;
         const double* col = src + basis_index(i0, j, r);
+        // n is padded to whole tiles in the norm arrays, so the pair load is always in bounds
+        const double2 pv1 = *reinterpret_cast<const double2*>(vn1 + j);
+        const double2 pv2 = *reinterpret_cast<const double2*>(vn2 + j);
         int k = 0;
         for (; k + 8 <= L; k += 8) {
             double2 a[8];
@@ -200,10 +203,10 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, 
         for (int e = 0; e < 2; ++e) {
             const int64_t jj = j + e;
             if (jj >= n) break;
-            double v1 = vn1[jj];
+            double v1 = e ? pv1.y : pv1.x;
             if (v1 < 0.0) continue;                 // already a pivot
             if (v1 != 0.0 && L > 0) {
-                const double v2 = vn2[jj];
+                const double v2 = e ? pv2.y : pv2.x;
                 if (downdate(e ? y1 : y0, v1, v2)) {
                     v1 = last_row ? 0.0 : recompute_norm(col + e, L, t, &P->V[0][0], P->tau);
                     vn2[jj] = v1;
@@ -249,6 +252,7 @@ qr_apply1_kernel(const double* __restrict__ src, double* __restrict__ dst, int64
         if (j >= n) continue;
         const double* col = src + tile * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + threadIdx.x;
         double* outp = dst + tile * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + threadIdx.x;
+        const double pv1 = vn1[j], pv2 = vn2[j];
         double c[LMAX];
 #pragma unroll
         for (int k = 0; k < LMAX; ++k) c[k] = (k < L) ? ldg_stream(col + k * OMB_TB) : 0.0;
@@ -263,10 +267,10 @@ qr_apply1_kernel(const double* __restrict__ src, double* __restrict__ dst, int64
             c[k] = fma(-tw, s_v[k], c[k]);
             if (k < L) stg_stream(outp + k * OMB_TB, c[k]);
         }
-        double v1 = vn1[j];
+        double v1 = pv1;
         if (v1 >= 0.0) {
             if (v1 != 0.0) {
-                const double v2 = vn2[j];
+                const double v2 = pv2;
                 if (downdate(rij, v1, v2)) {
                     double sq = 0.0;
 #pragma unroll
@@ -351,6 +355,16 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
         const int64_t tbase = (j0 >> 7) * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + (j0 & (OMB_TB - 1));
         const double* in = src + tbase + (2 * p) * OMB_TB + cq;
         double* out = dst + tbase + (2 * p) * OMB_TB + cq;
+        // norms of the columns this lane owns (p == tp), fetched up front so that the down-date at
+        // the end of the tile does not add a dependent round trip to HBM
+        double pv1[NG], pv2[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int64_t j = j0 + 8 * g + cq;
+            const bool owner = (p == tp) && (j < n);
+            pv1[g] = owner ? vn1[j] : -1.0;
+            pv2[g] = owner ? vn2[j] : 1.0;
+        }
         double c[LG][NG][2];
 #pragma unroll
         for (int G = 0; G < LG; ++G)
@@ -414,12 +428,9 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
         for (int g = 0; g < NG; ++g) {
             const int64_t j = j0 + 8 * g + cq;
             const bool owner = (p == tp) && (j < n);
-            double v1 = owner ? vn1[j] : -1.0;
+            double v1 = pv1[g];
             bool redo = false;
-            if (owner && v1 > 0.0) {
-                const double v2 = vn2[j];
-                redo = downdate(rij[g], v1, v2);
-            }
+            if (owner && v1 > 0.0) redo = downdate(rij[g], v1, pv2[g]);
             if (__any_sync(0xFFFFFFFFu, redo)) {
                 // exact trailing norm: each of the column's 4 lanes sums its rows, then combine
                 double sq = 0.0;
