@@ -109,6 +109,24 @@ int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* 
              void* d_ws, int block, int64_t index_base, int64_t* d_piv, double* d_rdiag,
              double* d_gap, void* stream);
 
+/* Multi-rank stepping interface (one process per GPU).  Rank g holds cells [cell0, cell0+n_c_loc) of
+ * every feature (n = F*n_c_loc local rows); per pivot step the caller all-gathers one record of
+ * omb_qrcp_record_doubles() doubles per rank (NCCL), everything else stays on the device:
+ *     omb_qrcp_mr_start(...)                          norms, position maps, step-0 candidates
+ *     for i in 0..s-1:  omb_qrcp_mr_local(i) -> d_rec ; all-gather -> d_recs ; omb_qrcp_mr_step(i)
+ * Every rank takes the same decision (records are scanned in rank order, ties by LAPACK position)
+ * and receives the same d_piv (GLOBAL row indices), d_rdiag, d_gap. */
+int64_t omb_qrcp_record_doubles(void);
+int omb_qrcp_mr_start(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, void* d_ws,
+                      int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world, void* stream);
+int omb_qrcp_mr_local(const double* d_Ut, const double* d_work, int64_t n, int64_t r, void* d_ws,
+                      int block, int64_t i, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank,
+                      int world, double* d_rec, void* stream);
+int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, int64_t r, int64_t s, void* d_ws,
+                     int block, int64_t i, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank,
+                     int world, const double* d_recs, int64_t* d_piv, double* d_rdiag, double* d_gap,
+                     void* stream);
+
 /* ---- K8/K9: train = row gather (replaces the dense C.dot(Ur), C.dot(X_cnt);
  *      sparse_sensing.py:797, :573).  d_Theta is s x r row-major, d_cnt_s may be NULL. -------- */
 int omb_gather_rows(const double* d_Ut, int64_t r, const int64_t* d_piv, int64_t s,

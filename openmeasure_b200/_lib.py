@@ -27,6 +27,11 @@ SIGNATURES = {
     "omb_backproject": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "omb_qrcp_ws_bytes": (_i64, [_i64, _i64]),
     "omb_qrcp": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
+    "omb_qrcp_record_doubles": (_i64, []),
+    "omb_qrcp_mr_start": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "omb_qrcp_mr_local": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "omb_qrcp_mr_step": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _i64, _i64, _i64, _i64, _int, _int, _vp,
+                                 _vp, _vp, _vp, _vp]),
     "omb_gather_rows": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "omb_modes_to_rows": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "omb_rows_to_modes": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -1,0 +1,135 @@
+"""Tiny communicator abstraction for the row-sharded path (one process per GPU).
+
+Only small, fixed-size objects ever cross ranks (F*4 block statistics, the m x m Gram, one
+record per pivot step, the s x r Theta), always as an all-gather followed by a fixed-order
+combination, so every rank computes bit-identical results:
+
+    SingleComm      world = 1, no communication
+    TorchDistComm   torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests)
+    ThreadComm      G ranks emulated by G threads of one process (single-GPU tests of the
+                    multi-rank numerics; kernels of all ranks are issued on the same stream, so
+                    no kernel ever waits on another rank's kernel)
+"""
+import threading
+
+import torch
+
+
+class SingleComm:
+    world = 1
+    rank = 0
+
+    def allgather(self, t):
+        """(world, numel) tensor holding every rank's flattened t, in rank order."""
+        return t.reshape(1, -1)
+
+    def bcast(self, t, src=0):
+        return t
+
+
+class TorchDistComm(SingleComm):
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def allgather(self, t):
+        flat = t.contiguous().reshape(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=flat.dtype, device=flat.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view(self.world, flat.numel())
+
+    def bcast(self, t, src=0):
+        gsrc = src if self.group is None else self.dist.get_global_rank(self.group, src)
+        self.dist.broadcast(t, gsrc, group=self.group)
+        return t
+
+
+class _ThreadShared:
+    def __init__(self, world):
+        self.slots = [None] * world
+        self.barrier = threading.Barrier(world)
+
+
+class ThreadComm(SingleComm):
+    """Create with ThreadComm.make(world) -> list of per-rank communicators."""
+
+    def __init__(self, shared, rank, world):
+        self.shared, self.rank, self.world = shared, rank, world
+
+    @classmethod
+    def make(cls, world):
+        shared = _ThreadShared(world)
+        return [cls(shared, r, world) for r in range(world)]
+
+    def allgather(self, t):
+        sh = self.shared
+        sh.slots[self.rank] = t.contiguous().reshape(-1)
+        sh.barrier.wait()
+        out = torch.stack(list(sh.slots))
+        sh.barrier.wait()
+        return out
+
+    def bcast(self, t, src=0):
+        g = self.allgather(t)
+        t.copy_(g[src].view_as(t))
+        return t
+
+
+def combine_block_stats(gathered, F, sq):
+    """Fixed-order (rank 0..G-1) combination of per-rank block statistics (world, F*4):
+    columns {sum, min, max, sqdev} per feature.  sq selects which columns are combined."""
+    g = gathered.view(gathered.shape[0], F, 4)
+    out = g[0].clone()
+    if not sq:
+        acc = g[0, :, 0].clone()
+        for k in range(1, g.shape[0]):
+            acc = acc + g[k, :, 0]
+        out[:, 0] = acc
+        out[:, 1] = g[:, :, 1].min(dim=0).values
+        out[:, 2] = g[:, :, 2].max(dim=0).values
+    else:
+        acc = g[0, :, 3].clone()
+        for k in range(1, g.shape[0]):
+            acc = acc + g[k, :, 3]
+        out[:, 3] = acc
+    return out.reshape(-1).contiguous()
+
+
+def ordered_sum(gathered):
+    """Sum over ranks in rank order (identical bits on every rank)."""
+    acc = gathered[0].clone()
+    for k in range(1, gathered.shape[0]):
+        acc = acc + gathered[k]
+    return acc
+
+
+class ShardLayout:
+    """Cells [cell0, cell0 + n_c_loc) of every one of the F features live on this rank."""
+
+    def __init__(self, F, cells_per_rank, rank):
+        self.F = int(F)
+        self.cells = [int(c) for c in cells_per_rank]
+        self.rank = int(rank)
+        self.n_c = sum(self.cells)
+        self.offsets = [sum(self.cells[:k]) for k in range(len(self.cells))]
+        self.n_c_loc = self.cells[self.rank]
+        self.cell0 = self.offsets[self.rank]
+
+    def to_global(self, local_rows):
+        f = local_rows // self.n_c_loc
+        return f * self.n_c + self.cell0 + (local_rows - f * self.n_c_loc)
+
+    def owner_and_local(self, global_rows):
+        """(owner rank, local row on the owner) of global rows (tensors or numpy arrays)."""
+        f = global_rows // self.n_c
+        c = global_rows - f * self.n_c
+        owner = (c * 0)
+        local = (c * 0)
+        for k, (off, cnt) in enumerate(zip(self.offsets, self.cells)):
+            inside = (c >= off) & (c < off + cnt)
+            owner = owner + inside * k
+            local = local + inside * (f * cnt + (c - off))
+        return owner, local

@@ -168,42 +168,64 @@ backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, i
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fr = lane & 3, fc = lane >> 2;
     const int64_t ntiles = basis_tiles(n);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    constexpr int KU = 6;                      // k-steps per chunk: 2*KU loads per lane in flight
+    const int nch = (mp + 4 * KU - 1) / (4 * KU);
+
+    // software pipeline in registers: the raw X values of the next chunk (possibly of the next
+    // tile) are requested before the current chunk is multiplied
+    struct Rows { bool ok0, ok1; double c0, c1, s0, s1; const double* x0; const double* x1; };
+    auto rows_of = [&](int64_t tile) {
+        Rows R;
         const int64_t rowb = tile * OMB_TB + warp * 16;
         const int64_t r0 = rowb + fc, r1 = rowb + 8 + fc;
-        const bool ok0 = r0 < n, ok1 = r1 < n;
-        const double c0 = (ok0 && cnt) ? cnt[r0] : 0.0, c1 = (ok1 && cnt) ? cnt[r1] : 0.0;
-        const double s0 = (ok0 && scl) ? scl[r0 / n_c] : 1.0, s1 = (ok1 && scl) ? scl[r1 / n_c] : 1.0;
-        const double* x0 = X + r0 * m + fr;
-        const double* x1 = X + r1 * m + fr;
+        R.ok0 = r0 < n; R.ok1 = r1 < n;
+        R.c0 = (R.ok0 && cnt) ? cnt[r0] : 0.0; R.c1 = (R.ok1 && cnt) ? cnt[r1] : 0.0;
+        R.s0 = (R.ok0 && scl) ? scl[r0 / n_c] : 1.0; R.s1 = (R.ok1 && scl) ? scl[r1 / n_c] : 1.0;
+        R.x0 = X + r0 * m + fr; R.x1 = X + r1 * m + fr;
+        return R;
+    };
+    auto fetch = [&](const Rows& R, int ch, double (&v0)[KU], double (&v1)[KU]) {
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            const int k0 = ch * 4 * KU + 4 * u;
+            const bool kin = (k0 + fr) < m;
+            v0[u] = (R.ok0 && kin) ? R.x0[k0] : R.c0;     // (value - cnt) == 0 outside the matrix
+            v1[u] = (R.ok1 && kin) ? R.x1[k0] : R.c1;
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    Rows cur{};
+    double v0[KU], v1[KU];
+    if (tile < ntiles) { cur = rows_of(tile); fetch(cur, 0, v0, v1); }
+    while (tile < ntiles) {
         double acc[2][QB][2];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int b = 0; b < QB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-        constexpr int KU = 6;      // k-steps whose loads are issued together (bytes in flight)
-#pragma unroll 1
-        for (int kc = 0; kc < mp; kc += 4 * KU) {
-            double a0[KU], a1[KU];
+        const int64_t ntile = tile + gridDim.x;
+        Rows nxt = cur;
+        for (int ch = 0; ch < nch; ++ch) {
+            double w0[KU], w1[KU];
+            const bool last = (ch + 1 == nch);
+            if (!last) fetch(cur, ch + 1, w0, w1);
+            else if (ntile < ntiles) { nxt = rows_of(ntile); fetch(nxt, 0, w0, w1); }
 #pragma unroll
             for (int u = 0; u < KU; ++u) {
-                const int k0 = kc + 4 * u;
-                const bool kin = (k0 + fr) < m;
-                a0[u] = (ok0 && kin) ? x0[k0] - c0 : 0.0;
-                a1[u] = (ok1 && kin) ? x1[k0] - c1 : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                const int k0 = kc + 4 * u;
+                const int k0 = ch * 4 * KU + 4 * u;
                 if (k0 < mp) {
+                    const double a0 = v0[u] - cur.c0, a1 = v1[u] - cur.c1;
 #pragma unroll
                     for (int b = 0; b < QB; ++b) {
                         const double bv = sW[(k0 + fr) * LDW + b * 8 + fc];
-                        dmma884(acc[0][b][0], acc[0][b][1], a0[u], bv);
-                        dmma884(acc[1][b][0], acc[1][b][1], a1[u], bv);
+                        dmma884(acc[0][b][0], acc[0][b][1], a0, bv);
+                        dmma884(acc[1][b][0], acc[1][b][1], a1, bv);
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < KU; ++u) { v0[u] = w0[u]; v1[u] = w1[u]; }
         }
         // the previous tile's bulk store must have finished reading sC before it is overwritten
         if (threadIdx.x == 0) tma_store_wait_read();
@@ -212,12 +234,12 @@ backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, i
         for (int b = 0; b < QB; ++b) {
             const int q = b * 8 + 2 * fr;
             if (q < r) {
-                sC[q * OMB_TB + warp * 16 + fc] = acc[0][b][0] / s0;
-                sC[q * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][0] / s1;
+                sC[q * OMB_TB + warp * 16 + fc] = acc[0][b][0] / cur.s0;
+                sC[q * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][0] / cur.s1;
             }
             if (q + 1 < r) {
-                sC[(q + 1) * OMB_TB + warp * 16 + fc] = acc[0][b][1] / s0;
-                sC[(q + 1) * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][1] / s1;
+                sC[(q + 1) * OMB_TB + warp * 16 + fc] = acc[0][b][1] / cur.s0;
+                sC[(q + 1) * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][1] / cur.s1;
             }
         }
         fence_proxy_async();
@@ -231,6 +253,8 @@ backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, i
             for (int q = 0; q < r; ++q) { const double u = sC[q * OMB_TB + threadIdx.x]; nrm = fma(u, u, nrm); }
             vn[tile * OMB_TB + threadIdx.x] = sqrt(nrm);
         }
+        cur = nxt;
+        tile = ntile;
     }
     if (threadIdx.x == 0) tma_store_wait_read();
 }

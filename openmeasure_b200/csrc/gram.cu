@@ -136,14 +136,22 @@ gram_tile_kernel(const double* __restrict__ X, int64_t n_c, int m, const double*
 // Warps are combined in a fixed order through shared memory; the CTA's partial goes out in the
 // 64 x 64 tile format of the general kernel and is reduced by the same fixed-order pass.
 // ---------------------------------------------------------------------------------------------
-constexpr int GS_THREADS = 256;
+constexpr int GS_WARPS = 8;                       // consumer warps: warp w owns k-step w of every chunk
+constexpr int GS_THREADS = (GS_WARPS + 1) * 32;   // + one producer warp driving the TMA ring
+constexpr int GS_CH = 4 * GS_WARPS;               // rows per chunk
+constexpr int GS_STAGES = 4;
 
 template <int NB>
 __global__ void __launch_bounds__(GS_THREADS)
 gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double* __restrict__ cnt,
                   int64_t rows_per_split, int splits, double* __restrict__ part)
 {
-    __shared__ double s_acc[GT * GT];
+    // ring of GS_STAGES chunks: [GS_CH rows x m] of X followed by the chunk's GS_CH centring values
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[GS_STAGES], empty_bar[GS_STAGES];
+    const int stage_doubles = ((GS_CH * m + 1) & ~1) + GS_CH;      // keeps every stage 16-byte aligned
+    double* s_acc = smem + GS_STAGES * stage_doubles;              // [GT][GT] final combination
+
     const int split = blockIdx.x, f = blockIdx.y;
     const int64_t row_lo = (int64_t)split * rows_per_split;
     int64_t row_hi = row_lo + rows_per_split;
@@ -151,57 +159,99 @@ gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double
     const double* Xf = X + (int64_t)f * n_c * m;
     const double* cf = cnt ? cnt + (int64_t)f * n_c : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int fr = lane & 3, fc = lane >> 2;
-    constexpr int NW = GS_THREADS / 32;
+    const int nchunks = (int)ceil_div(row_hi - row_lo, GS_CH);
 
-    double c[NB][NB][2];
-#pragma unroll
-    for (int a = 0; a < NB; ++a)
-#pragma unroll
-        for (int b = 0; b < NB; ++b) c[a][b][0] = c[a][b][1] = 0.0;
-
-    bool colok[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) colok[b] = (8 * b + fc) < m;
-
-    // warp w takes the k-steps w, w + NW, ... of the CTA's row range (4 rows per step), two at a time
-    for (int64_t k0 = row_lo + 4 * warp; k0 < row_hi; k0 += 8 * NW) {
-        double a[2][NB];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int64_t row = k0 + 4 * NW * u + fr;
-            const bool rok = row < row_hi;
-            const double cv = (rok && cf) ? cf[row] : 0.0;
-            const double* xr = Xf + row * m + fc;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) a[u][b] = (rok && colok[b]) ? xr[8 * b] - cv : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int bi = 0; bi < NB; ++bi)
-#pragma unroll
-                for (int bj = bi; bj < NB; ++bj) dmma884(c[bi][bj][0], c[bi][bj][1], a[u][bi], a[u][bj]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], GS_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-
-    // fixed-order combination of the warps
-    for (int e = threadIdx.x; e < GT * GT; e += GS_THREADS) s_acc[e] = 0.0;
     __syncthreads();
-    for (int w = 0; w < NW; ++w) {
-        if (warp == w) {
+
+    if (warp == GS_WARPS) {
+        // ---------------- producer warp ----------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % GS_STAGES;
+            if (c >= GS_STAGES) mbar_wait(&empty_bar[s], ((c / GS_STAGES) - 1) & 1);
+            const int64_t k0 = row_lo + (int64_t)c * GS_CH;
+            const int rows = (int)((row_hi - k0) < GS_CH ? (row_hi - k0) : GS_CH);
+            double* dstX = smem + s * stage_doubles;
+            double* dstC = dstX + ((GS_CH * m + 1) & ~1);
+            const double* srcX = Xf + k0 * m;
+            const uint32_t bytesX = (uint32_t)(rows * m * sizeof(double));
+            const bool bulk_ok = ((reinterpret_cast<uintptr_t>(srcX) & 15) == 0) && ((bytesX & 15) == 0) &&
+                                 (!cf || ((reinterpret_cast<uintptr_t>(cf + k0) & 15) == 0 && (rows & 1) == 0));
+            if (bulk_ok) {
+                if (lane == 0) {
+                    const uint32_t bytesC = cf ? (uint32_t)(rows * sizeof(double)) : 0u;
+                    mbar_expect_tx(&full_bar[s], bytesX + bytesC);
+                    tma_load_bulk(dstX, srcX, bytesX, &full_bar[s]);
+                    if (cf) tma_load_bulk(dstC, cf + k0, bytesC, &full_bar[s]);
+                }
+            } else {
+                // ragged or unaligned chunk: the producer warp copies it itself
+                for (int e = lane; e < rows * m; e += 32) dstX[e] = srcX[e];
+                if (cf) for (int e = lane; e < rows; e += 32) dstC[e] = cf[k0 + e];
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        const int fr = lane & 3, fc = lane >> 2;
+        double c[NB][NB][2];
+#pragma unroll
+        for (int a = 0; a < NB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+        bool colok[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) colok[b] = (8 * b + fc) < m;
+
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % GS_STAGES;
+            mbar_wait(&full_bar[s], (ch / GS_STAGES) & 1);
+            const double* sX = smem + s * stage_doubles;
+            const double* sC = sX + ((GS_CH * m + 1) & ~1);
+            const int64_t k0 = row_lo + (int64_t)ch * GS_CH;
+            const int rowc = 4 * warp + fr;                         // row inside the chunk
+            const bool rok = (k0 + rowc) < row_hi;
+            const double cv = (rok && cf) ? sC[rowc] : 0.0;
+            double a[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? sX[rowc * m + 8 * b + fc] - cv : 0.0;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
 #pragma unroll
             for (int bi = 0; bi < NB; ++bi)
 #pragma unroll
-                for (int bj = bi; bj < NB; ++bj) {
-                    const int i = bi * 8 + fc, j = bj * 8 + 2 * fr;
-                    s_acc[i * GT + j] += c[bi][bj][0];
-                    s_acc[i * GT + j + 1] += c[bi][bj][1];
-                }
+                for (int bj = bi; bj < NB; ++bj) dmma884(c[bi][bj][0], c[bi][bj][1], a[bi], a[bj]);
         }
-        __syncthreads();
+
+        // fixed-order combination of the consumer warps (named barrier 1: consumers only)
+        for (int e = threadIdx.x; e < GT * GT; e += GS_WARPS * 32) s_acc[e] = 0.0;
+        asm volatile("bar.sync 1, %0;" ::"n"(GS_WARPS * 32) : "memory");
+        for (int w = 0; w < GS_WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                    for (int bj = bi; bj < NB; ++bj) {
+                        const int i = bi * 8 + fc, j = bj * 8 + 2 * fr;
+                        s_acc[i * GT + j] += c[bi][bj][0];
+                        s_acc[i * GT + j + 1] += c[bi][bj][1];
+                    }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(GS_WARPS * 32) : "memory");
+        }
+        double* out = part + ((int64_t)f * splits + split) * (GT * GT);
+        for (int e = threadIdx.x; e < GT * GT; e += GS_WARPS * 32) out[e] = s_acc[e];
     }
-    double* out = part + ((int64_t)f * splits + split) * (GT * GT);
-    for (int e = threadIdx.x; e < GT * GT; e += GS_THREADS) out[e] = s_acc[e];
+}
+
+static size_t gram_small_smem(int m)
+{
+    const int stage_doubles = ((GS_CH * m + 1) & ~1) + GS_CH;
+    return sizeof(double) * ((size_t)GS_STAGES * stage_doubles + GT * GT);
 }
 
 typedef void (*GramSmallFn)(const double*, int64_t, int, const double*, int64_t, int, double*);
@@ -226,7 +276,7 @@ static GramPlan gram_small_plan(int64_t F, int64_t n_c)
     p.T = 1;
     p.ntiles = 1;
     int64_t splits = ceil_div((int64_t)sm_count() * 2, F);
-    const int64_t unit = 8 * (GS_THREADS / 32);                 // rows per CTA round
+    const int64_t unit = GS_CH;                                 // rows per chunk
     int64_t max_splits = ceil_div(n_c, 4 * unit);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -294,8 +344,10 @@ extern "C" int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, co
     if (m <= 64) {
         p = gram_small_plan(F, n_c);
         dim3 grid((unsigned)p.splits, (unsigned)F);
-        pick_gram_small((int)m)<<<grid, GS_THREADS, 0, st>>>(d_X, n_c, (int)m, d_cnt, p.rows_per_split, p.splits,
-                                                             (double*)d_ws);
+        GramSmallFn fn = pick_gram_small((int)m);
+        const size_t smem = gram_small_smem((int)m);
+        OMB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<grid, GS_THREADS, smem, st>>>(d_X, n_c, (int)m, d_cnt, p.rows_per_split, p.splits, (double*)d_ws);
         rc = check_launch("gram_small_kernel");
     } else {
         p = gram_plan(F, n_c, m);

@@ -48,7 +48,23 @@ struct Panel {
     double q[QR_RMAX];            // q = Q e_t   ->  R[i, j] = q . A[i0:, j]
     int64_t posmap[QR_RMAX];      // current LAPACK position of original column c < s
     int64_t col_at_pos[QR_RMAX];  // original column now at position k < s
+    int ncand;                    // argmax records left by the last pass kernel (multi-rank path)
 };
+
+constexpr int QR_REC = 8 + QR_RMAX;   // doubles per cross-rank record: header + pivot column tail
+
+// Row sharding across ranks: every rank holds cells [cell0, cell0 + n_c_loc) of every feature, so
+// local row j = f * n_c_loc + c is global row f * n_c + cell0 + c.  world == 1: identity.
+struct Shard {
+    int64_t n_c_loc, n_c, cell0;
+    int rank, world;
+};
+__device__ __forceinline__ int64_t glob_index(int64_t j, const Shard& sh)
+{
+    if (sh.world == 1) return j;
+    const int64_t f = j / sh.n_c_loc;
+    return f * sh.n_c + sh.cell0 + (j - f * sh.n_c_loc);
+}
 
 __device__ __forceinline__ bool cand_better(double b1, int64_t k1, double b2, int64_t k2)
 {
@@ -67,6 +83,18 @@ __device__ __forceinline__ void cand_push(Cand& a, double v, int64_t idx, int64_
 {
     if (cand_better(v, key, a.best, a.key)) { a.second = a.best; a.best = v; a.idx = idx; a.key = key; }
     else a.second = fmax(a.second, v);
+}
+// push with the LAPACK position key computed only when it can matter (v >= current best)
+__device__ __forceinline__ void cand_push_lazy(Cand& a, double v, int64_t j, const Shard& sh, const Panel* P,
+                                               int64_t s_total)
+{
+    if (v >= a.best) {
+        const int64_t g = glob_index(j, sh);
+        const int64_t key = g < s_total ? P->posmap[g] : g;
+        cand_push(a, v, j, key);
+    } else {
+        a.second = fmax(a.second, v);
+    }
 }
 __device__ __forceinline__ Cand cand_shfl_xor(const Cand& a, int o)
 {
@@ -168,7 +196,7 @@ constexpr int GV_THREADS = 256;
 __global__ void __launch_bounds__(GV_THREADS)
 qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, int t, int last_row,
                const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-               int64_t s_total, Cand* __restrict__ cand)
+               int64_t s_total, Shard sh, Cand* __restrict__ cand)
 {
     __shared__ double s_q[QR_RMAX];
     __shared__ Cand s_c[GV_THREADS / 32];
@@ -213,12 +241,14 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, 
                 }
                 vn1[jj] = v1;
             }
-            const int64_t key = jj < s_total ? P->posmap[jj] : jj;
-            cand_push(best, v1, jj, key);
+            cand_push_lazy(best, v1, jj, sh, P, s_total);
         }
     }
     best = cand_block_reduce(best, s_c);
-    if (threadIdx.x == 0) cand[blockIdx.x] = best;
+    if (threadIdx.x == 0) {
+        cand[blockIdx.x] = best;
+        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,7 +264,7 @@ template <int LMAX>
 __global__ void __launch_bounds__(AR_THREADS, ar_min_blocks(LMAX))
 qr_apply1_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L,
                  const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-                 int64_t s_total, Cand* __restrict__ cand)
+                 int64_t s_total, Shard sh, Cand* __restrict__ cand)
 {
     __shared__ double s_v[LMAX];
     __shared__ double s_tau;
@@ -280,16 +310,18 @@ qr_apply1_kernel(const double* __restrict__ src, double* __restrict__ dst, int64
                 }
                 vn1[j] = v1;
             }
-            const int64_t key = j < s_total ? P->posmap[j] : j;
-            cand_push(best, v1, j, key);
+            cand_push_lazy(best, v1, j, sh, P, s_total);
         }
     }
     best = cand_block_reduce(best, s_c);
-    if (threadIdx.x == 0) cand[blockIdx.x] = best;
+    if (threadIdx.x == 0) {
+        cand[blockIdx.x] = best;
+        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
+    }
 }
 
 typedef void (*Apply1Fn)(const double*, double*, int64_t, int, int, int, const Panel*, double*, double*, int64_t,
-                         Cand*);
+                         Shard, Cand*);
 static Apply1Fn pick_apply1(int L, int* lmax)
 {
     if (L <= 16) { *lmax = 16; return qr_apply1_kernel<16>; }
@@ -320,7 +352,7 @@ template <int LG, int NG>
 __global__ void __launch_bounds__(AM_THREADS)
 qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L, int t,
                     const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-                    int64_t s_total, Cand* __restrict__ cand)
+                    int64_t s_total, Shard sh, Cand* __restrict__ cand)
 {
     constexpr int LP = LG * 8;                 // padded rows
     constexpr int SVT = LP + 2;                // row stride of sVt [refl][row]: == 2 (mod 8)
@@ -450,17 +482,19 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
             }
             if (owner && v1 >= 0.0) {
                 vn1[j] = v1;
-                const int64_t key = j < s_total ? P->posmap[j] : j;
-                cand_push(best, v1, j, key);
+                cand_push_lazy(best, v1, j, sh, P, s_total);
             }
         }
     }
     best = cand_block_reduce(best, s_c);
-    if (threadIdx.x == 0) cand[blockIdx.x] = best;
+    if (threadIdx.x == 0) {
+        cand[blockIdx.x] = best;
+        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
+    }
 }
 
 typedef void (*ApplyMmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
-                           int64_t, Cand*);
+                           int64_t, Shard, Cand*);
 
 // tensor-path apply kernel for L rows (L <= 256); *ng = column groups per warp
 static ApplyMmaFn pick_apply_mma(int L, int* ng)
@@ -497,11 +531,37 @@ __device__ __forceinline__ double block_sum(double x, double* s_red)
     return s;
 }
 
+// multi-rank step A (1 CTA): local argmax + the winner's trailing column -> one record
+__global__ void __launch_bounds__(PN_THREADS)
+qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, const double* __restrict__ src, int r,
+                int i0, int L, Shard sh, double* __restrict__ rec)
+{
+    __shared__ Cand s_c[PN_THREADS / 32];
+    __shared__ int64_t s_p;
+    Cand c = cand_empty();
+    const int ncand = P->ncand;
+    for (int e = threadIdx.x; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
+    c = cand_block_reduce(c, s_c);
+    if (threadIdx.x == 0) {
+        s_p = c.idx;
+        rec[0] = c.best;
+        rec[1] = c.second;
+        rec[2] = __longlong_as_double(c.key);
+        rec[3] = __longlong_as_double(c.idx >= 0 ? glob_index(c.idx, sh) : -1);
+        rec[4] = __longlong_as_double(c.idx);
+    }
+    __syncthreads();
+    const int64_t p = s_p;
+    for (int k = threadIdx.x; k < L; k += PN_THREADS)
+        rec[8 + k] = (p >= 0) ? src[basis_index(i0 + k, p, r)] : 0.0;
+}
+
+template <bool MULTI>
 __global__ void __launch_bounds__(PN_THREADS)
 qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand, const double* __restrict__ src,
-                int r, int i0, int L, int i, int t, int seq_norm, int64_t s_total, int64_t index_base,
-                double* __restrict__ vn1, int64_t* __restrict__ piv, double* __restrict__ rdiag,
-                double* __restrict__ gap)
+                int r, int i0, int L, int i, int t, int seq_norm, int64_t s_total, int64_t index_base, Shard sh,
+                const double* __restrict__ recs, double* __restrict__ vn1, int64_t* __restrict__ piv,
+                double* __restrict__ rdiag, double* __restrict__ gap)
 {
     __shared__ Cand s_c[PN_THREADS / 32];
     __shared__ double s_V[QR_BMAX][QR_RMAX];   // earlier reflectors of this block (rows < t), then v_t
@@ -523,20 +583,40 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         s_T[a][b] = P->T[a][b];
     }
 
-    // 1. global argmax over the pass kernel's records
-    Cand c = cand_empty();
-    for (int e = threadIdx.x; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
-    c = cand_block_reduce(c, s_c);
-    if (threadIdx.x == 0) s_p = c.idx;
-    __syncthreads();
-    const int64_t p = s_p;
-
-    // 2. pivot column tail at block start (all threads) while thread 0 does LAPACK's bookkeeping
-    {
-        const double* col = src + basis_index(i0, p, r);
+    Cand c = cand_empty();       // winner: idx = GLOBAL row index, key = LAPACK position
+    int64_t p_local = -1;        // the winner's local column, -1 if another rank owns it
+    if (!MULTI) {
+        // 1. global argmax over the pass kernel's records
+        for (int e = threadIdx.x; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
+        c = cand_block_reduce(c, s_c);
+        if (threadIdx.x == 0) s_p = c.idx;
+        __syncthreads();
+        p_local = s_p;
+        // 2. pivot column tail at block start
+        const double* col = src + basis_index(i0, p_local, r);
         for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = col[(int64_t)k * OMB_TB];
+    } else {
+        // 1. winner among the ranks' records (fixed order: identical decision on every rank)
+        if (threadIdx.x == 0) {
+            int wr = -1;
+            for (int g = 0; g < sh.world; ++g) {
+                const double* rc = recs + (int64_t)g * QR_REC;
+                Cand b;
+                b.best = rc[0]; b.second = rc[1];
+                b.key = __double_as_longlong(rc[2]); b.idx = __double_as_longlong(rc[3]);
+                if (b.idx < 0) continue;
+                const bool wins = cand_better(b.best, b.key, c.best, c.key);
+                cand_merge(c, b);
+                if (wins) { wr = g; p_local = (g == sh.rank) ? __double_as_longlong(rc[4]) : -1; }
+            }
+            s_p = wr;
+        }
+        __syncthreads();
+        const double* rc = recs + (int64_t)s_p * QR_REC + 8;
+        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = rc[k];
     }
     if (threadIdx.x == 0) {
+        const int64_t p = c.idx;         // global row index (single rank: local == global)
         piv[i] = p + index_base;
         gap[i] = (c.second < 0.0 || c.best <= 0.0) ? 1.0 : (c.best - c.second) / c.best;
         // LAPACK's swap of positions i <-> pos(p): the column sitting at position i moves to pos(p)
@@ -548,7 +628,7 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         }
         P->col_at_pos[i] = p;
         if (p < s_total) P->posmap[p] = i;
-        vn1[p] = -1.0;                   // never a candidate again
+        if (p_local >= 0) vn1[p_local] = -1.0;     // never a candidate again
     }
     __syncthreads();
     if (t > 0) {
@@ -693,86 +773,182 @@ extern "C" int64_t omb_qrcp_ws_bytes(int64_t n, int64_t r)
     return qr_ws_layout(n, nullptr, nullptr);
 }
 
+namespace omb {
+
+static int64_t gemv_grid(int64_t n)
+{
+    int64_t g = ceil_div(basis_tiles(n) * (OMB_TB / 2), GV_THREADS);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g > QR_NCAND) g = QR_NCAND;
+    return g;
+}
+
+// norms -> vn1/vn2, position maps, and the step-0 argmax records.  Returns the record count (< 0: error code)
+static int qr_start(const double* d_Ut, int64_t n, int r, int64_t s, const double* d_vn, const QrWs& w, Shard sh,
+                    cudaStream_t st, int* ncand)
+{
+    const int sms = sm_count();
+    int rc;
+    const double* vn = d_vn;
+    int64_t g = ceil_div(n, 256);
+    if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
+    if (!vn) {
+        qr_norms_kernel<<<(unsigned)g, 256, 0, st>>>(d_Ut, n, r, w.vn_tmp);
+        if ((rc = check_launch("qr_norms_kernel"))) return rc;
+        vn = w.vn_tmp;
+    }
+    qr_init_kernel<<<(unsigned)g, 256, 0, st>>>(vn, n, w.vn1, w.vn2, w.panel);
+    if ((rc = check_launch("qr_init_kernel"))) return rc;
+    // step-0 argmax: a read-only pass over zero rows leaves the norms untouched
+    const int64_t gv = gemv_grid(n);
+    qr_gemv_kernel<<<(unsigned)gv, GV_THREADS, 0, st>>>(d_Ut, n, r, 0, 0, 0, 0, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+    if ((rc = check_launch("qr_gemv_kernel"))) return rc;
+    *ncand = (int)gv;
+    return 0;
+}
+
+// the pass that follows the panel of step i (block-local step t of the block starting at i0)
+static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t s, int block, int i0, int t,
+                   const QrWs& w, Shard sh, cudaStream_t st, int* ncand)
+{
+    const int sms = sm_count();
+    const int L = r - i0;
+    const int64_t ntiles = basis_tiles(n);
+    int rc;
+    if (t == block - 1) {
+        int64_t g;
+        int lmax = 0, ng = 0;
+        Apply1Fn f1 = (block == 1) ? pick_apply1(L, &lmax) : nullptr;
+        if (f1) {
+            g = ntiles;
+            if (g > (int64_t)sms * ar_min_blocks(lmax)) g = (int64_t)sms * ar_min_blocks(lmax);   // one wave
+            if (g > QR_NCAND) g = QR_NCAND;
+            f1<<<(unsigned)g, AR_THREADS, 0, st>>>(src, d_work, n, r, i0, L, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+            if ((rc = check_launch("qr_apply1_kernel"))) return rc;
+        } else {
+            // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
+            //  tensor-path rounding instead of the oracle's fma order)
+            ApplyMmaFn fm = pick_apply_mma(L, &ng);
+            g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
+            if (g > (int64_t)sms * 3) g = (int64_t)sms * 3;
+            if (g > QR_NCAND) g = QR_NCAND;
+            fm<<<(unsigned)g, AM_THREADS, 0, st>>>(src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+            if ((rc = check_launch("qr_apply_mma_kernel"))) return rc;
+        }
+        *ncand = (int)g;
+    } else {
+        const int64_t gv = gemv_grid(n);
+        qr_gemv_kernel<<<(unsigned)gv, GV_THREADS, 0, st>>>(src, n, r, i0, L, t, (t + 1 == L) ? 1 : 0, w.panel, w.vn1,
+                                                           w.vn2, s, sh, w.cand);
+        if ((rc = check_launch("qr_gemv_kernel"))) return rc;
+        *ncand = (int)gv;
+    }
+    return 0;
+}
+
+static int qr_check(const void* d_Ut, const void* d_work, const void* d_ws, int64_t n, int64_t r, int64_t s, int block)
+{
+    OMB_CHECK_ARG(d_Ut && d_work && d_ws, "null pointer");
+    OMB_CHECK_ARG(n > 0 && r > 0 && s > 0, "non-positive size");
+    OMB_CHECK_ARG(r <= QR_RMAX, "r exceeds the supported number of modes (256)");
+    OMB_CHECK_ARG(s <= r, "s must be <= r");
+    OMB_CHECK_ARG(block >= 1 && block <= QR_BMAX, "block must be in [1, 8]");
+    OMB_CHECK_ARG((((uintptr_t)d_Ut | (uintptr_t)d_work) & 15) == 0, "basis pointers must be 16-byte aligned");
+    return 0;
+}
+
+}  // namespace omb
+
 extern "C" int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
                         void* d_ws, int block, int64_t index_base, int64_t* d_piv, double* d_rdiag, double* d_gap,
                         void* stream)
 {
-    OMB_CHECK_ARG(d_Ut && d_work && d_ws && d_piv && d_rdiag && d_gap, "null pointer");
-    OMB_CHECK_ARG(n > 0 && r > 0 && s > 0, "non-positive size");
-    OMB_CHECK_ARG(r <= QR_RMAX, "r exceeds the supported number of modes (256)");
-    OMB_CHECK_ARG(s <= r && s <= n, "s must be <= min(r, n)");
-    OMB_CHECK_ARG(block >= 1 && block <= QR_BMAX, "block must be in [1, 8]");
-    OMB_CHECK_ARG((((uintptr_t)d_Ut | (uintptr_t)d_work) & 15) == 0, "basis pointers must be 16-byte aligned");
+    int rc = qr_check(d_Ut, d_work, d_ws, n, r, s, block);
+    if (rc) return rc;
+    OMB_CHECK_ARG(d_piv && d_rdiag && d_gap, "null pointer");
+    OMB_CHECK_ARG(s <= n, "s must be <= n");
     cudaStream_t st = (cudaStream_t)stream;
     QrWs w;
     qr_ws_layout(n, &w, (char*)d_ws);
-    const int sms = sm_count();
     const int ri = (int)r;
-    int rc;
-
-    const double* vn = d_vn;
-    if (!vn) {
-        int64_t g = ceil_div(n, 256);
-        if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
-        qr_norms_kernel<<<(unsigned)g, 256, 0, st>>>(d_Ut, n, ri, w.vn_tmp);
-        if ((rc = check_launch("qr_norms_kernel"))) return rc;
-        vn = w.vn_tmp;
-    }
-    {
-        int64_t g = ceil_div(n, 256);
-        if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
-        qr_init_kernel<<<(unsigned)g, 256, 0, st>>>(vn, n, w.vn1, w.vn2, w.panel);
-        if ((rc = check_launch("qr_init_kernel"))) return rc;
-    }
-
-    const int64_t ntiles = basis_tiles(n);
-    int64_t gv_grid = ceil_div(ntiles * (OMB_TB / 2), GV_THREADS);
-    if (gv_grid > (int64_t)sms * 8) gv_grid = (int64_t)sms * 8;
-    if (gv_grid > QR_NCAND) gv_grid = QR_NCAND;
-
-    // step-0 argmax: a read-only pass over zero rows leaves the norms untouched
-    qr_gemv_kernel<<<(unsigned)gv_grid, GV_THREADS, 0, st>>>(d_Ut, n, ri, 0, 0, 0, 0, w.panel, w.vn1, w.vn2, s, w.cand);
-    if ((rc = check_launch("qr_gemv_kernel"))) return rc;
-    int ncand = (int)gv_grid;
-
+    Shard sh;
+    sh.n_c_loc = n; sh.n_c = n; sh.cell0 = 0; sh.rank = 0; sh.world = 1;
+    int ncand = 0;
+    if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, st, &ncand))) return rc;
     const double* src = d_Ut;   // trailing matrix as of the block start, rows i0..r-1
     int i0 = 0;
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        const int L = ri - i0;
-        qr_panel_kernel<<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, ncand, src, ri, i0, L, i, t, block == 1 ? 1 : 0, s,
-                                                   index_base, w.vn1, d_piv, d_rdiag, d_gap);
+        qr_panel_kernel<false><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, ncand, src, ri, i0, ri - i0, i, t,
+                                                          block == 1 ? 1 : 0, s, index_base, sh, nullptr, w.vn1, d_piv,
+                                                          d_rdiag, d_gap);
         if ((rc = check_launch("qr_panel_kernel"))) return rc;
         if (i == (int)s - 1) break;           // no further pivot needed: skip the last pass
-        if (t == block - 1) {
-            int64_t g;
-            int lmax = 0, ng = 0;
-            Apply1Fn f1 = (block == 1) ? pick_apply1(L, &lmax) : nullptr;
-            if (f1) {
-                g = ntiles;
-                if (g > (int64_t)sms * ar_min_blocks(lmax)) g = (int64_t)sms * ar_min_blocks(lmax);   // one wave
-                if (g > QR_NCAND) g = QR_NCAND;
-                f1<<<(unsigned)g, AR_THREADS, 0, st>>>(src, d_work, n, ri, i0, L, w.panel, w.vn1, w.vn2, s, w.cand);
-                if ((rc = check_launch("qr_apply1_kernel"))) return rc;
-            } else {
-                // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
-                //  tensor-path rounding instead of the oracle's fma order)
-                ApplyMmaFn fm = pick_apply_mma(L, &ng);
-                g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
-                if (g > (int64_t)sms * 3) g = (int64_t)sms * 3;
-                if (g > QR_NCAND) g = QR_NCAND;
-                fm<<<(unsigned)g, AM_THREADS, 0, st>>>(src, d_work, n, ri, i0, L, t, w.panel, w.vn1, w.vn2, s, w.cand);
-                if ((rc = check_launch("qr_apply_mma_kernel"))) return rc;
-            }
-            ncand = (int)g;
-            src = d_work;
-            i0 = i + 1;
-        } else {
-            qr_gemv_kernel<<<(unsigned)gv_grid, GV_THREADS, 0, st>>>(src, n, ri, i0, L, t, (t + 1 == L) ? 1 : 0, w.panel,
-                                                                    w.vn1, w.vn2, s, w.cand);
-            if ((rc = check_launch("qr_gemv_kernel"))) return rc;
-            ncand = (int)gv_grid;
-        }
+        if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
+        if (t == block - 1) { src = d_work; i0 = i + 1; }
     }
     return 0;
+}
+
+// ---- multi-rank stepping interface (one process per GPU; the caller all-gathers the records) ----
+static Shard make_shard(int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world)
+{
+    Shard sh;
+    sh.n_c_loc = n_c_loc; sh.n_c = n_c; sh.cell0 = cell0; sh.rank = rank; sh.world = world;
+    return sh;
+}
+
+extern "C" int64_t omb_qrcp_record_doubles(void) { return QR_REC; }
+
+extern "C" int omb_qrcp_mr_start(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, void* d_ws,
+                                 int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world, void* stream)
+{
+    OMB_CHECK_ARG(d_Ut && d_ws, "null pointer");
+    OMB_CHECK_ARG(n > 0 && r > 0 && r <= QR_RMAX && s > 0 && s <= r, "bad size");
+    OMB_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && n_c_loc > 0 && n % n_c_loc == 0, "bad shard");
+    QrWs w;
+    qr_ws_layout(n, &w, (char*)d_ws);
+    int ncand = 0;
+    return qr_start(d_Ut, n, (int)r, s, d_vn, w, make_shard(n_c_loc, n_c, cell0, rank, world), (cudaStream_t)stream,
+                    &ncand);
+}
+
+// step i, part A: this rank's best candidate and its trailing column -> d_rec (QR_REC doubles)
+extern "C" int omb_qrcp_mr_local(const double* d_Ut, const double* d_work, int64_t n, int64_t r, void* d_ws, int block,
+                                 int64_t i, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world,
+                                 double* d_rec, void* stream)
+{
+    OMB_CHECK_ARG(d_Ut && d_work && d_ws && d_rec, "null pointer");
+    OMB_CHECK_ARG(block >= 1 && block <= QR_BMAX && i >= 0 && i < r, "bad step");
+    QrWs w;
+    qr_ws_layout(n, &w, (char*)d_ws);
+    const int i0 = (int)(i / block) * block;
+    const double* src = i0 == 0 ? d_Ut : d_work;
+    qr_local_kernel<<<1, PN_THREADS, 0, (cudaStream_t)stream>>>(w.panel, w.cand, src, (int)r, i0, (int)r - i0,
+                                                               make_shard(n_c_loc, n_c, cell0, rank, world), d_rec);
+    return check_launch("qr_local_kernel");
+}
+
+// step i, part B: the winner among the `world` gathered records, reflector, then this rank's pass
+extern "C" int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, int64_t r, int64_t s, void* d_ws,
+                                int block, int64_t i, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world,
+                                const double* d_recs, int64_t* d_piv, double* d_rdiag, double* d_gap, void* stream)
+{
+    int rc = qr_check(d_Ut, d_work, d_ws, n, r, s, block);
+    if (rc) return rc;
+    OMB_CHECK_ARG(d_recs && d_piv && d_rdiag && d_gap && i >= 0 && i < s, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    QrWs w;
+    qr_ws_layout(n, &w, (char*)d_ws);
+    const Shard sh = make_shard(n_c_loc, n_c, cell0, rank, world);
+    const int ri = (int)r;
+    const int i0 = (int)(i / block) * block, t = (int)i - i0;
+    const double* src = i0 == 0 ? d_Ut : d_work;
+    qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, (int)i, t, 0, s, 0, sh,
+                                                     d_recs, w.vn1, d_piv, d_rdiag, d_gap);
+    if ((rc = check_launch("qr_panel_kernel"))) return rc;
+    if (i == s - 1) return 0;
+    int ncand = 0;
+    return qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand);
 }

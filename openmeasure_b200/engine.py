@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import comm as _comm
 
 SCALE_CODES = {"std": 0, "none": 1, "pareto": 2, "vast": 3, "range": 4, "level": 5, "max": 6,
                "variance": 7, "poisson": 8, "l2-norm": 9}
@@ -52,7 +53,7 @@ def tiles_for(n):
 
 
 class Engine:
-    def __init__(self, X_dev, n_features, group=None):
+    def __init__(self, X_dev, n_features, group=None, comm=None):
         require_cuda()
         assert X_dev.is_cuda and X_dev.dtype == torch.float64 and X_dev.dim() == 2
         if not X_dev.is_contiguous():
@@ -63,32 +64,30 @@ class Engine:
         self.n_loc, self.m = (int(v) for v in X_dev.shape)
         assert self.n_loc % self.F == 0
         self.n_c_loc = self.n_loc // self.F
-        self.group = group
-        self.world = 1
-        self.rank = 0
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                 and group is not False):
-            import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(group) > 1:
-                self.world = dist.get_world_size(group)
-                self.rank = dist.get_rank(group)
+        if comm is None:
+            comm = _comm.SingleComm()
+            if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                    and torch.distributed.get_world_size(group) > 1:
+                comm = _comm.TorchDistComm(group)
+        self.comm = comm
+        self.world, self.rank = comm.world, comm.rank
         if self.world > 1:
-            import torch.distributed as dist
-            counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
-            counts[self.rank] = self.n_c_loc
-            dist.all_reduce(counts, group=self.group)
-            self.cells_per_rank = [int(c) for c in counts.cpu()]
+            mine = torch.tensor([self.n_c_loc], dtype=torch.int64, device=self.dev)
+            cells = [int(c) for c in comm.allgather(mine).view(-1).cpu()]
         else:
-            self.cells_per_rank = [self.n_c_loc]
-        self.n_c = sum(self.cells_per_rank)             # global cells per feature
-        self.cell0 = sum(self.cells_per_rank[: self.rank])
+            cells = [self.n_c_loc]
+        self.layout = _comm.ShardLayout(self.F, cells, self.rank)
+        self.n_c = self.layout.n_c                      # global cells per feature
+        self.cell0 = self.layout.cell0
         self.cnt = None
         self.scl = None
         self.Ut = None
         self.vn = None
         self.r = None
         self.ntiles = tiles_for(self.n_loc)
-        self.timings = {}
+
+    def _shard_args(self):
+        return (self.n_c_loc, self.n_c, self.cell0, self.rank, self.world)
 
     # ------------------------------------------------------------------------------------ K1
     def stats(self, scale_type="std", axis_cnt=1):
@@ -106,37 +105,16 @@ class Engine:
         count = self.n_c * m
         _lib.call("omb_block_stats", _p(self.X), F, blk, 0, count, _p(stats), _p(ws), st)
         if self.world > 1:
-            stats = self._combine_stats(stats, sq=False)
+            stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=False)
         if scale_type in NEEDS_SQDEV:
             _lib.call("omb_block_stats", _p(self.X), F, blk, 1, count, _p(stats), _p(ws), st)
             if self.world > 1:
-                stats = self._combine_stats(stats, sq=True)
+                stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=True)
         scl = torch.empty(F, dtype=torch.float64, device=self.dev)
         _lib.call("omb_finalize_scale", _p(stats), F, count, SCALE_CODES[scale_type], _p(scl),
                   1 if axis_cnt is None else 0, _p(cnt), ncl, st)
         self.cnt, self.scl, self.block_stats = cnt, scl, stats
         return cnt, scl
-
-    def _combine_stats(self, stats, sq):
-        """Fixed-order (rank 0..G-1) combination of the per-rank block statistics."""
-        import torch.distributed as dist
-        allst = torch.empty(self.world * stats.numel(), dtype=torch.float64, device=self.dev)
-        dist.all_gather_into_tensor(allst, stats, group=self.group)
-        allst = allst.view(self.world, self.F, 4)
-        out = stats.view(self.F, 4).clone()
-        if not sq:
-            acc = allst[0, :, 0].clone()
-            for g in range(1, self.world):
-                acc = acc + allst[g, :, 0]
-            out[:, 0] = acc
-            out[:, 1] = allst[:, :, 1].min(dim=0).values
-            out[:, 2] = allst[:, :, 2].max(dim=0).values
-        else:
-            acc = allst[0, :, 3].clone()
-            for g in range(1, self.world):
-                acc = acc + allst[g, :, 3]
-            out[:, 3] = acc
-        return out.reshape(-1).contiguous()
 
     def set_scale_feature(self, f, value):
         self.scl[f] = value
@@ -151,19 +129,16 @@ class Engine:
         _lib.call("omb_gram", _p(self.X), F, ncl, m, _p(self.cnt if centred else None), _p(Gf), _p(ws), st)
         G = torch.empty(m, m, dtype=torch.float64, device=self.dev)
         _lib.call("omb_gram_combine", _p(Gf), F, m, _p(self.scl if scaled else None), _p(G), st)
-        if self.world > 1:
-            import torch.distributed as dist
-            gathered = torch.empty(self.world, m, m, dtype=torch.float64, device=self.dev)
-            dist.all_gather_into_tensor(gathered, G, group=self.group)
-            G = gathered[0].clone()
-            for g in range(1, self.world):          # fixed order: identical bits on every rank
-                G = G + gathered[g]
+        if self.world > 1:                          # fixed order: identical bits on every rank
+            G = _comm.ordered_sum(self.comm.allgather(G)).view(m, m)
         return G
 
-    @staticmethod
-    def eig_pod(G):
+    def eig_pod(self, G):
         """m x m eigensolve -> singular values (descending) and right singular vectors."""
         w, V = torch.linalg.eigh(G)
+        if self.world > 1:                          # every rank must rotate with the very same V
+            w = self.comm.bcast(w.contiguous(), 0)
+            V = self.comm.bcast(V.contiguous(), 0)
         w = torch.flip(w, dims=(0,))
         V = torch.flip(V, dims=(1,)).contiguous()
         S = torch.sqrt(torch.clamp(w, min=0.0))
@@ -218,9 +193,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ K6
     def qrcp(self, s=None, block=8):
-        """Pivoted QR over the candidate rows; returns (piv, rdiag, gap) as device tensors."""
-        if self.world > 1:
-            raise NotImplementedError("multi-rank placement is driven by openmeasure_b200.parallel")
+        """Pivoted QR over the candidate rows; returns (piv, rdiag, gap) as device tensors.
+        Multi-rank: piv holds GLOBAL row indices and is identical on every rank."""
         r = self.r
         s = r if s is None else int(s)
         block = max(1, min(8, int(block)))
@@ -229,18 +203,41 @@ class Engine:
         piv = torch.empty(s, dtype=torch.int64, device=self.dev)
         rdiag = torch.empty(s, dtype=torch.float64, device=self.dev)
         gap = torch.empty(s, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_qrcp", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(work), _p(ws),
-                  int(block), 0, _p(piv), _p(rdiag), _p(gap), _stream())
+        if self.world == 1:
+            _lib.call("omb_qrcp", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(work), _p(ws),
+                      block, 0, _p(piv), _p(rdiag), _p(gap), _stream())
+            return piv, rdiag, gap
+        L = _lib.load()
+        nrec = int(L.omb_qrcp_record_doubles())
+        rec = torch.zeros(nrec, dtype=torch.float64, device=self.dev)
+        sh = self._shard_args()
+        _lib.call("omb_qrcp_mr_start", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(ws), *sh, _stream())
+        for i in range(s):
+            _lib.call("omb_qrcp_mr_local", _p(self.Ut), _p(work), self.n_loc, r, _p(ws), block, i, *sh,
+                      _p(rec), _stream())
+            recs = self.comm.allgather(rec)           # one small record per rank per pivot step
+            _lib.call("omb_qrcp_mr_step", _p(self.Ut), _p(work), self.n_loc, r, s, _p(ws), block, i, *sh,
+                      _p(recs), _p(piv), _p(rdiag), _p(gap), _stream())
         return piv, rdiag, gap
 
     # ------------------------------------------------------------------------------- K8 - K11
     def gather(self, piv_dev):
+        """Theta = rows `piv` (global indices) of U_r, and the centring values at those rows."""
         s = int(piv_dev.numel())
         Theta = torch.empty(s, self.r, dtype=torch.float64, device=self.dev)
         cnt_s = torch.empty(s, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_gather_rows", _p(self.Ut), self.r, _p(piv_dev), s, _p(Theta),
-                  _p(self.cnt), _p(cnt_s), _stream())
-        return Theta, cnt_s
+        if self.world == 1:
+            _lib.call("omb_gather_rows", _p(self.Ut), self.r, _p(piv_dev), s, _p(Theta),
+                      _p(self.cnt), _p(cnt_s), _stream())
+            return Theta, cnt_s
+        owner, local = self.layout.owner_and_local(piv_dev)
+        mine = owner == self.rank
+        loc = torch.where(mine, local, torch.zeros_like(local)).contiguous()
+        _lib.call("omb_gather_rows", _p(self.Ut), self.r, _p(loc), s, _p(Theta), _p(self.cnt), _p(cnt_s),
+                  _stream())
+        both = torch.cat([Theta * mine.unsqueeze(1), (cnt_s * mine).unsqueeze(1)], dim=1)
+        both = _comm.ordered_sum(self.comm.allgather(both)).view(s, self.r + 1)   # one non-zero term per row
+        return both[:, : self.r].contiguous(), both[:, self.r].contiguous()
 
     def ols_predict(self, Y_dev, cnt_s, scl_s, PinvT):
         N, s = (int(v) for v in Y_dev.shape)

@@ -107,9 +107,11 @@ class ROM:
 
     # ------------------------------------------------------------------ device plumbing
     @classmethod
-    def from_device(cls, X_dev, n_features, xyz=None, group=None):
-        """Extension: build on an HBM-resident shard (torch CUDA float64 (F*n_c_loc, m)); with
-        torch.distributed initialised each rank passes its own cells of every feature."""
+    def from_device(cls, X_dev, n_features, xyz=None, group=None, comm=None):
+        """Extension: build on an HBM-resident shard (torch CUDA float64 (F*n_c_loc, m)).  With
+        torch.distributed initialised (one process per GPU) each rank passes its own cells
+        [c0, c0 + n_c_loc) of every feature; pivots / C then refer to GLOBAL row indices
+        f * n_c + c, Theta / predict are replicated, reconstruct returns the local rows."""
         self = cls.__new__(cls)
         if type(n_features) is not int:
             raise TypeError('The parameter n_features is not an integer.')
@@ -118,7 +120,7 @@ class ROM:
         self.X = None
         self.n_features = n_features
         self.xyz = xyz
-        self._eng = _eng.Engine(X_dev, n_features, group=group)
+        self._eng = _eng.Engine(X_dev, n_features, group=group, comm=comm)
         self.n_points = self._eng.n_c_loc
         self._host = {}
         return self
@@ -136,7 +138,9 @@ class ROM:
         return self._eng
 
     def _n_rows(self):
-        return self.X.shape[0] if self.X is not None else self._eng.n_loc
+        if self.X is not None:
+            return self.X.shape[0]
+        return self._eng.F * self._eng.n_c          # global rows (== local rows on a single rank)
 
     # ------------------------------------------------------------------ lazy host mirrors
     @property

@@ -357,3 +357,63 @@ def test_large_properties(torch_cuda):
     y2[:, 0] = 2 * y[:, 0] - spr.X_cnt[spr.qr_pivots, 0]
     a2, _ = spr.predict(y2)
     np.testing.assert_allclose(a2, 2 * a, rtol=1e-9, atol=1e-9 * np.abs(a).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# row-sharded (multi-rank) path: G ranks emulated by G threads on this one GPU (ThreadComm), every
+# kernel issued on the same stream.  Results must not depend on the number of ranks.
+# ---------------------------------------------------------------------------------------------
+def _run_ranks(torch, X, F, cells, r, block):
+    import threading
+    from openmeasure_b200 import comm as C
+    n_c = sum(cells)
+    comms = C.ThreadComm.make(len(cells))
+    out = [None] * len(cells)
+    err = []
+
+    def run(rk):
+        try:
+            lay = C.ShardLayout(F, cells, rk)
+            rows = lay.to_global(torch.arange(F * cells[rk])).numpy()
+            Xl = torch.from_numpy(np.ascontiguousarray(X[rows])).cuda()
+            spr = _sps().SPR.from_device(Xl, F, comm=comms[rk])
+            spr.fit(select_modes='number', n_modes=r)
+            Cm = spr.optimal_placement(block=block)
+            spr.train(Cm)
+            y = np.zeros((r, 3))
+            y[:, 0] = X[Cm.pivots, 2]
+            y[:, 2] = Cm.pivots // n_c
+            a, _ = spr.predict(y)
+            out[rk] = dict(piv=Cm.pivots.copy(), S=spr.Sigma_r.copy(), Theta=spr.Theta.copy(), a=a,
+                           rec=spr.reconstruct(a), rows=rows, shape=Cm.shape, scl=spr.X_scl[::cells[rk], 0].copy())
+        except Exception as e:          # pragma: no cover
+            err.append(e)
+            comms[rk].shared.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(k,)) for k in range(len(cells))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if err:
+        raise err[0]
+    return out
+
+
+@pytest.mark.parametrize("cells,block", [([400, 300], 4), ([200, 260, 240], 1), ([350, 350], 8)])
+def test_multirank_matches_single_rank(torch_cuda, cells, block):
+    from oracle import pod_oracle as po, synth as osynth
+    F, m, r = 3, 24, 10
+    n_c = sum(cells)
+    X = osynth.snapshots(F, n_c, m, r)
+    ref = po.placement_pipeline(X, F, r)
+    one = _run_ranks(torch_cuda, X, F, [n_c], r, block)[0]
+    np.testing.assert_array_equal(one["piv"], ref["piv"])
+    outs = _run_ranks(torch_cuda, X, F, cells, r, block)
+    full = np.zeros((F * n_c, 1))
+    for o in outs:
+        assert o["shape"] == (r, F * n_c)
+        np.testing.assert_array_equal(o["piv"], ref["piv"])                 # global pivots, every rank
+        np.testing.assert_allclose(o["S"], ref["Sigma_r"], rtol=RTOL)
+        np.testing.assert_allclose(o["scl"], ref["X_scl"][::n_c, 0], rtol=1e-14)
+        np.testing.assert_allclose(np.abs(o["Theta"]), np.abs(one["Theta"]), rtol=0, atol=1e-10)
+        full[o["rows"]] = o["rec"]
+    np.testing.assert_allclose(full, one["rec"], rtol=1e-9)
