@@ -127,6 +127,18 @@ int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, int64_t r, i
                      int world, const double* d_recs, int64_t* d_piv, double* d_rdiag, double* d_gap,
                      void* stream);
 
+/* Same placement with the per-step exchange done by the kernels themselves over NVLink peer memory
+ * (stores into every peer's symmetric buffer + a step flag; no NCCL call and no host round trip
+ * inside the loop).  d_peers: device array of `world` buffer addresses (entry `rank` == d_mine), each
+ * omb_qrcp_p2p_buffer_doubles(world) doubles, zero-filled once; epoch: strictly increasing per
+ * call and identical on every rank.  After synchronising, a non-zero int64 at
+ * d_mine + 2*world*record_doubles + 3*world means a peer never answered (10 s timeout). */
+int64_t omb_qrcp_p2p_buffer_doubles(int world);
+int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
+                 void* d_ws, int block, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world,
+                 const void* d_peers, double* d_mine, int64_t epoch, int64_t* d_piv, double* d_rdiag,
+                 double* d_gap, void* stream);
+
 /* ---- K8/K9: train = row gather (replaces the dense C.dot(Ur), C.dot(X_cnt);
  *      sparse_sensing.py:797, :573).  d_Theta is s x r row-major, d_cnt_s may be NULL. -------- */
 int omb_gather_rows(const double* d_Ut, int64_t r, const int64_t* d_piv, int64_t s,

@@ -47,6 +47,34 @@ class TorchDistComm(SingleComm):
         return t
 
 
+_P2P_CACHE = {}
+
+
+def p2p_state(comm, device, ndoubles):
+    """Symmetric (peer-mapped over NVLink) FP64 buffer shared by the ranks of `comm`, created once
+    per process group: dict(buf, peers_dev, epoch) or None when unavailable / disabled
+    (OMB_QR_EXCHANGE=nccl).  Collective: every rank must call it at the same point."""
+    import os
+    if not isinstance(comm, TorchDistComm) or os.environ.get("OMB_QR_EXCHANGE", "p2p") != "p2p":
+        return None
+    key = (id(comm.group) if comm.group is not None else 0, comm.world)
+    st = _P2P_CACHE.get(key)
+    if st is None or st["buf"].numel() < ndoubles:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = comm.group if comm.group is not None else comm.dist.group.WORLD
+            buf = symm_mem.empty(int(ndoubles), dtype=torch.float64, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group=grp)
+            torch.cuda.synchronize(device)
+            comm.dist.barrier(group=comm.group)
+            st = {"buf": buf, "hdl": hdl, "peers_dev": int(hdl.buffer_ptrs_dev), "epoch": 0}
+        except Exception as e:          # symmetric memory not available on this system
+            st = {"buf": torch.empty(0), "hdl": None, "peers_dev": 0, "epoch": 0, "error": repr(e)}
+        _P2P_CACHE[key] = st
+    return st if st["hdl"] is not None else None
+
+
 class _ThreadShared:
     def __init__(self, world):
         self.slots = [None] * world

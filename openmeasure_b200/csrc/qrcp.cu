@@ -531,12 +531,70 @@ __device__ __forceinline__ double block_sum(double x, double* s_red)
     return s;
 }
 
-// multi-rank step A (1 CTA): local argmax + the winner's trailing column -> one record
+// ---- peer-to-peer exchange over NVLink (symmetric memory): every rank owns a buffer laid out as
+//   recs [2][world][QR_REC] doubles | step flags [2][world] int64 | barrier flags [world] int64 | error int64
+// and holds the device addresses of all ranks' buffers.  A record is published by storing it into
+// slot [parity][my_rank] of EVERY peer's buffer, fencing, and then storing the step flag; the
+// consumer spins on its OWN copy of the flags.  Flag values only grow (epoch * 4096 + step + 1).
+struct P2P {
+    double* const* peers;     // device array of `world` buffer addresses (NULL: host-gathered path)
+    double* mine;             // this rank's buffer
+    int64_t epoch;
+};
+__device__ __forceinline__ double* p2p_rec(double* buf, int world, int parity, int src)
+{
+    return buf + ((int64_t)parity * world + src) * QR_REC;
+}
+__device__ __forceinline__ int64_t* p2p_flags(double* buf, int world)
+{
+    return reinterpret_cast<int64_t*>(buf + (int64_t)2 * world * QR_REC);
+}
+__device__ __forceinline__ void st_release_sys(int64_t* p, int64_t v)
+{
+    asm volatile("st.release.sys.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int64_t ld_acquire_sys(const int64_t* p)
+{
+    int64_t v;
+    asm volatile("ld.acquire.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= want; gives up after ~10 s and raises the buffer's error word
+__device__ __forceinline__ void p2p_wait(const int64_t* p, int64_t want, int64_t* err)
+{
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_sys(p) < want) {
+        if ((++spins & 0x3FFu) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 10000000000ull) { *err = 1; break; }
+        }
+    }
+}
+
+// all ranks have finished the previous placement before anyone reuses the record slots
+__global__ void qr_p2p_barrier_kernel(P2P pp, int rank, int world)
+{
+    int64_t* myflags = p2p_flags(pp.mine, world);
+    const int g = threadIdx.x;
+    if (g < world) {
+        int64_t* peer_flags = p2p_flags(pp.peers[g], world);
+        st_release_sys(peer_flags + 2 * world + rank, pp.epoch);
+    }
+    __syncthreads();
+    if (g < world) p2p_wait(myflags + 2 * world + g, pp.epoch, myflags + 3 * world);
+}
+
+// multi-rank step A (1 CTA): local argmax + the winner's trailing column -> one record, written to
+// `rec` (host-gathered path) or published to every peer (P2P path)
 __global__ void __launch_bounds__(PN_THREADS)
 qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, const double* __restrict__ src, int r,
-                int i0, int L, Shard sh, double* __restrict__ rec)
+                int i0, int L, int step, Shard sh, double* __restrict__ rec, P2P pp)
 {
     __shared__ Cand s_c[PN_THREADS / 32];
+    __shared__ double s_rec[QR_REC];
     __shared__ int64_t s_p;
     Cand c = cand_empty();
     const int ncand = P->ncand;
@@ -544,23 +602,40 @@ qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, cons
     c = cand_block_reduce(c, s_c);
     if (threadIdx.x == 0) {
         s_p = c.idx;
-        rec[0] = c.best;
-        rec[1] = c.second;
-        rec[2] = __longlong_as_double(c.key);
-        rec[3] = __longlong_as_double(c.idx >= 0 ? glob_index(c.idx, sh) : -1);
-        rec[4] = __longlong_as_double(c.idx);
+        s_rec[0] = c.best;
+        s_rec[1] = c.second;
+        s_rec[2] = __longlong_as_double(c.key);
+        s_rec[3] = __longlong_as_double(c.idx >= 0 ? glob_index(c.idx, sh) : -1);
+        s_rec[4] = __longlong_as_double(c.idx);
+        s_rec[5] = s_rec[6] = s_rec[7] = 0.0;
     }
     __syncthreads();
     const int64_t p = s_p;
     for (int k = threadIdx.x; k < L; k += PN_THREADS)
-        rec[8 + k] = (p >= 0) ? src[basis_index(i0 + k, p, r)] : 0.0;
+        s_rec[8 + k] = (p >= 0) ? src[basis_index(i0 + k, p, r)] : 0.0;
+    __syncthreads();
+    if (pp.peers == nullptr) {
+        for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) rec[k] = s_rec[k];
+        return;
+    }
+    const int parity = step & 1;
+    for (int g = 0; g < sh.world; ++g) {
+        double* dst = p2p_rec(pp.peers[g], sh.world, parity, sh.rank);
+        for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) dst[k] = s_rec[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < sh.world) {
+        int64_t* peer_flags = p2p_flags(pp.peers[threadIdx.x], sh.world);
+        st_release_sys(peer_flags + parity * sh.world + sh.rank, pp.epoch * 4096 + step + 1);
+    }
 }
 
 template <bool MULTI>
 __global__ void __launch_bounds__(PN_THREADS)
 qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand, const double* __restrict__ src,
                 int r, int i0, int L, int i, int t, int seq_norm, int64_t s_total, int64_t index_base, Shard sh,
-                const double* __restrict__ recs, double* __restrict__ vn1, int64_t* __restrict__ piv,
+                const double* recs, P2P pp, double* __restrict__ vn1, int64_t* __restrict__ piv,
                 double* __restrict__ rdiag, double* __restrict__ gap)
 {
     __shared__ Cand s_c[PN_THREADS / 32];
@@ -596,24 +671,32 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         const double* col = src + basis_index(i0, p_local, r);
         for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = col[(int64_t)k * OMB_TB];
     } else {
+        if (pp.peers != nullptr) {
+            // P2P path: wait until every rank's record of this step has landed in MY buffer
+            int64_t* myflags = p2p_flags(pp.mine, sh.world);
+            if (threadIdx.x < sh.world)
+                p2p_wait(myflags + (i & 1) * sh.world + threadIdx.x, pp.epoch * 4096 + i + 1, myflags + 3 * sh.world);
+            __syncthreads();
+            recs = p2p_rec(pp.mine, sh.world, i & 1, 0);
+        }
         // 1. winner among the ranks' records (fixed order: identical decision on every rank)
         if (threadIdx.x == 0) {
             int wr = -1;
             for (int g = 0; g < sh.world; ++g) {
                 const double* rc = recs + (int64_t)g * QR_REC;
                 Cand b;
-                b.best = rc[0]; b.second = rc[1];
-                b.key = __double_as_longlong(rc[2]); b.idx = __double_as_longlong(rc[3]);
+                b.best = __ldcg(rc + 0); b.second = __ldcg(rc + 1);
+                b.key = __double_as_longlong(__ldcg(rc + 2)); b.idx = __double_as_longlong(__ldcg(rc + 3));
                 if (b.idx < 0) continue;
                 const bool wins = cand_better(b.best, b.key, c.best, c.key);
                 cand_merge(c, b);
-                if (wins) { wr = g; p_local = (g == sh.rank) ? __double_as_longlong(rc[4]) : -1; }
+                if (wins) { wr = g; p_local = (g == sh.rank) ? __double_as_longlong(__ldcg(rc + 4)) : -1; }
             }
             s_p = wr;
         }
         __syncthreads();
         const double* rc = recs + (int64_t)s_p * QR_REC + 8;
-        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = rc[k];
+        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = __ldcg(rc + k);
     }
     if (threadIdx.x == 0) {
         const int64_t p = c.idx;         // global row index (single rank: local == global)
@@ -881,8 +964,8 @@ extern "C" int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, con
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
         qr_panel_kernel<false><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, ncand, src, ri, i0, ri - i0, i, t,
-                                                          block == 1 ? 1 : 0, s, index_base, sh, nullptr, w.vn1, d_piv,
-                                                          d_rdiag, d_gap);
+                                                          block == 1 ? 1 : 0, s, index_base, sh, nullptr, P2P{nullptr, nullptr, 0},
+                                                          w.vn1, d_piv, d_rdiag, d_gap);
         if ((rc = check_launch("qr_panel_kernel"))) return rc;
         if (i == (int)s - 1) break;           // no further pivot needed: skip the last pass
         if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
@@ -925,8 +1008,9 @@ extern "C" int omb_qrcp_mr_local(const double* d_Ut, const double* d_work, int64
     qr_ws_layout(n, &w, (char*)d_ws);
     const int i0 = (int)(i / block) * block;
     const double* src = i0 == 0 ? d_Ut : d_work;
-    qr_local_kernel<<<1, PN_THREADS, 0, (cudaStream_t)stream>>>(w.panel, w.cand, src, (int)r, i0, (int)r - i0,
-                                                               make_shard(n_c_loc, n_c, cell0, rank, world), d_rec);
+    qr_local_kernel<<<1, PN_THREADS, 0, (cudaStream_t)stream>>>(w.panel, w.cand, src, (int)r, i0, (int)r - i0, (int)i,
+                                                               make_shard(n_c_loc, n_c, cell0, rank, world), d_rec,
+                                                               P2P{nullptr, nullptr, 0});
     return check_launch("qr_local_kernel");
 }
 
@@ -946,9 +1030,50 @@ extern "C" int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, i
     const int i0 = (int)(i / block) * block, t = (int)i - i0;
     const double* src = i0 == 0 ? d_Ut : d_work;
     qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, (int)i, t, 0, s, 0, sh,
-                                                     d_recs, w.vn1, d_piv, d_rdiag, d_gap);
+                                                     d_recs, P2P{nullptr, nullptr, 0}, w.vn1, d_piv, d_rdiag, d_gap);
     if ((rc = check_launch("qr_panel_kernel"))) return rc;
     if (i == s - 1) return 0;
     int ncand = 0;
     return qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand);
+}
+
+// ---- multi-rank placement with the per-step exchange done by the kernels themselves over NVLink
+// peer memory (no NCCL call, no host round trip inside the loop).  d_peers: device array of `world`
+// symmetric-buffer addresses (entry `rank` == d_mine), each omb_qrcp_p2p_buffer_doubles(world) doubles,
+// zero-filled once at allocation.  epoch: strictly increasing per call, identical on every rank.
+extern "C" int64_t omb_qrcp_p2p_buffer_doubles(int world) { return (int64_t)2 * world * QR_REC + 3 * world + 8; }
+
+extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
+                            void* d_ws, int block, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world,
+                            const void* d_peers, double* d_mine, int64_t epoch, int64_t* d_piv, double* d_rdiag,
+                            double* d_gap, void* stream)
+{
+    int rc = qr_check(d_Ut, d_work, d_ws, n, r, s, block);
+    if (rc) return rc;
+    OMB_CHECK_ARG(d_peers && d_mine && d_piv && d_rdiag && d_gap, "null pointer");
+    OMB_CHECK_ARG(world >= 2 && world <= 64 && rank >= 0 && rank < world && epoch > 0 && s < 4096, "bad p2p argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    QrWs w;
+    qr_ws_layout(n, &w, (char*)d_ws);
+    const Shard sh = make_shard(n_c_loc, n_c, cell0, rank, world);
+    const P2P pp{(double* const*)d_peers, d_mine, epoch};
+    const int ri = (int)r;
+    qr_p2p_barrier_kernel<<<1, 64, 0, st>>>(pp, rank, world);
+    if ((rc = check_launch("qr_p2p_barrier_kernel"))) return rc;
+    int ncand = 0;
+    if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, st, &ncand))) return rc;
+    const double* src = d_Ut;
+    int i0 = 0;
+    for (int i = 0; i < (int)s; ++i) {
+        const int t = i - i0;
+        qr_local_kernel<<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, src, ri, i0, ri - i0, i, sh, nullptr, pp);
+        if ((rc = check_launch("qr_local_kernel"))) return rc;
+        qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, i, t, 0, s, 0, sh,
+                                                         nullptr, pp, w.vn1, d_piv, d_rdiag, d_gap);
+        if ((rc = check_launch("qr_panel_kernel"))) return rc;
+        if (i == (int)s - 1) break;
+        if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
+        if (t == block - 1) { src = d_work; i0 = i + 1; }
+    }
+    return 0;
 }

@@ -86,6 +86,12 @@ class Engine:
         self.r = None
         self.ntiles = tiles_for(self.n_loc)
 
+    def check_p2p(self):
+        """Raise if a peer never answered during the last peer-memory placement."""
+        st = getattr(self, "_p2p_err", None)
+        if st is not None and st[0][st[1]:st[1] + 1].view(torch.int64).item() != 0:
+            raise _lib.OmbError("multi-rank placement: a peer rank did not publish its record (10 s timeout)")
+
     def _shard_args(self):
         return (self.n_c_loc, self.n_c, self.cell0, self.rank, self.world)
 
@@ -208,6 +214,15 @@ class Engine:
                       block, 0, _p(piv), _p(rdiag), _p(gap), _stream())
             return piv, rdiag, gap
         L = _lib.load()
+        p2p = _comm.p2p_state(self.comm, self.dev, int(L.omb_qrcp_p2p_buffer_doubles(self.world)))
+        if p2p is not None:
+            # the kernels exchange the per-step records themselves over NVLink peer memory
+            p2p["epoch"] += 1
+            _lib.call("omb_qrcp_p2p", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(work), _p(ws), block,
+                      *self._shard_args(), C.c_void_p(p2p["peers_dev"]), _p(p2p["buf"]), p2p["epoch"],
+                      _p(piv), _p(rdiag), _p(gap), _stream())
+            self._p2p_err = (p2p["buf"], 2 * self.world * int(L.omb_qrcp_record_doubles()) + 3 * self.world)
+            return piv, rdiag, gap
         nrec = int(L.omb_qrcp_record_doubles())
         rec = torch.zeros(nrec, dtype=torch.float64, device=self.dev)
         sh = self._shard_args()

@@ -366,6 +366,7 @@ class SPR(ROM):
             self._host.pop("Ur", None)
         piv, rdiag, gap = eng.qrcp(block=block)
         self.qr_pivots = piv.cpu().numpy()
+        eng.check_p2p()
         self.qr_rdiag = rdiag.cpu().numpy()
         self.qr_gap = gap.cpu().numpy()
         return SensorMatrix(self.qr_pivots, self._n_rows())
