@@ -45,9 +45,10 @@ enum {
 };
 
 /* ---- synthetic snapshots (no reference counterpart; DESIGN.md "Synthetic workload") -------- */
+int64_t omb_synth_ws_bytes(int64_t F, int64_t m, int64_t K);
 int omb_synth_fill(double* d_X, int64_t F, int64_t n_cells, int64_t cell0, int64_t ncell_loc,
                    int64_t m, int64_t K, uint64_t seed, const double* d_amp, const double* d_dec,
-                   double eps, void* stream);
+                   double eps, void* d_ws, void* stream);
 
 /* ---- K1: centring / scaling statistics (replaces np.average/np.std/np.max/np.min over the
  *      n_cells-row feature blocks, sparse_sensing.py:112-161) -------------------------------- */
@@ -85,6 +86,13 @@ int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double*
 /* G (m x m) = sum_f Gf[f] / scl[f]^2, fixed order. d_scl may be NULL (all ones). */
 int omb_gram_combine(const double* d_Gf, int64_t F, int64_t m, const double* d_scl, double* d_G,
                      void* stream);
+
+/* ---- S3: m x m symmetric eigensolve of the Gram matrix for few snapshots (m <= omb_eigh_max_m()):
+ *      one-CTA cyclic Jacobi; replaces the small dense part of dgesdd (sparse_sensing.py:272).
+ *      d_G row-major symmetric (upper triangle read), d_w eigenvalues DESCENDING, d_V[i*m + k] =
+ *      component i of eigenvector k, d_info (may be NULL) = sweeps used. */
+int omb_eigh_max_m(void);
+int omb_eigh_jacobi(const double* d_G, int64_t m, double* d_w, double* d_V, int* d_info, void* stream);
 
 /* ---- K5: back-projection U_r = X0 * W, W = V_r Sigma_r^-1 (m x r row-major), written mode-major,
  *      with the initial QRCP column norms vn[i] = ||U_r[i,:]||_2 fused (replaces U = Q*U_R inside

@@ -14,7 +14,8 @@ SIGNATURES = {
     "omb_last_error": (C.c_char_p, []),
     "omb_launch_count": (_i64, []),
     "omb_launch_count_reset": (None, []),
-    "omb_synth_fill": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _vp, _vp, _dbl, _vp]),
+    "omb_synth_ws_bytes": (_i64, [_i64, _i64, _i64]),
+    "omb_synth_fill": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _vp, _vp, _dbl, _vp, _vp]),
     "omb_row_means": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "omb_block_stats_ws_bytes": (_i64, [_i64, _i64]),
     "omb_block_stats": (_int, [_vp, _i64, _i64, _int, _i64, _vp, _vp, _vp]),
@@ -24,6 +25,8 @@ SIGNATURES = {
     "omb_gram_ws_bytes": (_i64, [_i64, _i64, _i64]),
     "omb_gram": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "omb_gram_combine": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "omb_eigh_max_m": (_int, []),
+    "omb_eigh_jacobi": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "omb_backproject": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "omb_qrcp_ws_bytes": (_i64, [_i64, _i64]),
     "omb_qrcp": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp]),

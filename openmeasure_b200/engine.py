@@ -140,19 +140,24 @@ class Engine:
         return G
 
     def eig_pod(self, G):
-        """m x m eigensolve -> singular values (descending) and right singular vectors."""
-        w, V = torch.linalg.eigh(G)
+        """m x m eigensolve -> singular values (descending) and right singular vectors (the
+        largest-magnitude component of each vector positive)."""
+        m = int(G.shape[0])
+        if m <= int(_lib.load().omb_eigh_max_m()):
+            w = torch.empty(m, dtype=torch.float64, device=self.dev)
+            V = torch.empty(m, m, dtype=torch.float64, device=self.dev)
+            _lib.call("omb_eigh_jacobi", _p(G.contiguous()), m, _p(w), _p(V), None, _stream())
+        else:
+            w, V = torch.linalg.eigh(G)
+            w = torch.flip(w, dims=(0,))
+            V = torch.flip(V, dims=(1,))
+            idx = torch.argmax(V.abs(), dim=0)
+            sgn = torch.sign(V[idx, torch.arange(m, device=V.device)])
+            V = (V * torch.where(sgn == 0, torch.ones_like(sgn), sgn)).contiguous()
         if self.world > 1:                          # every rank must rotate with the very same V
             w = self.comm.bcast(w.contiguous(), 0)
             V = self.comm.bcast(V.contiguous(), 0)
-        w = torch.flip(w, dims=(0,))
-        V = torch.flip(V, dims=(1,)).contiguous()
-        S = torch.sqrt(torch.clamp(w, min=0.0))
-        # deterministic sign: the largest-magnitude component of each right vector is positive
-        idx = torch.argmax(V.abs(), dim=0)
-        sgn = torch.sign(V[idx, torch.arange(V.shape[1], device=V.device)])
-        sgn = torch.where(sgn == 0, torch.ones_like(sgn), sgn)
-        return S, V * sgn
+        return torch.sqrt(torch.clamp(w, min=0.0)), V
 
     # ------------------------------------------------------------------------------------ K5
     def backproject(self, W, centred=True, scaled=True, norms=True):

@@ -34,6 +34,7 @@ def snapshots(F, n_cells, m, r, seed=SEED, cell0=0, ncell_loc=None, hard=False, 
     amp_d = torch.tensor(amp, dtype=torch.float64, device=dev)
     dec_d = torch.tensor(dec, dtype=torch.float64, device=dev)
     X = torch.empty(F * ncell_loc, m, dtype=torch.float64, device=dev)
+    ws = torch.empty(int(_lib.load().omb_synth_ws_bytes(F, m, K)), dtype=torch.uint8, device=dev)
     _lib.call("omb_synth_fill", _p(X), F, n_cells, cell0, ncell_loc, m, K, C.c_uint64(seed),
-              _p(amp_d), _p(dec_d), eps, _stream())
+              _p(amp_d), _p(dec_d), eps, _p(ws), _stream())
     return X

@@ -417,3 +417,37 @@ def test_multirank_matches_single_rank(torch_cuda, cells, block):
         np.testing.assert_allclose(np.abs(o["Theta"]), np.abs(one["Theta"]), rtol=0, atol=1e-10)
         full[o["rows"]] = o["rec"]
     np.testing.assert_allclose(full, one["rec"], rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# S3: one-CTA Jacobi eigensolver vs LAPACK (np.linalg.eigh), including the rank-deficient Gram of
+# row-centred data (sigma_m ~ 0) and graded spectra
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [1, 2, 5, 14, 41, 64])
+@pytest.mark.parametrize("kind", ["gram", "graded"])
+def test_eigh_jacobi_matches_lapack(torch_cuda, m, kind):
+    import ctypes as C
+    from openmeasure_b200 import _lib
+    torch = torch_cuda
+    rng = np.random.default_rng(100 * m + len(kind))
+    if kind == "gram":
+        X = rng.standard_normal((500, m))
+        X -= X.mean(axis=1, keepdims=True)          # row-centred: rank m - 1
+        G = X.T @ X
+    else:
+        Q, _ = np.linalg.qr(rng.standard_normal((m, m)))
+        G = (Q * np.logspace(0, -10, m)) @ Q.T
+        G = (G + G.T) / 2
+    Gd = torch.from_numpy(G).cuda()
+    w = torch.empty(m, dtype=torch.float64, device="cuda")
+    V = torch.empty(m, m, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("omb_eigh_jacobi", C.c_void_p(Gd.data_ptr()), m, C.c_void_p(w.data_ptr()), C.c_void_p(V.data_ptr()),
+              C.c_void_p(info.data_ptr()), None)
+    w, V = w.cpu().numpy(), V.cpu().numpy()
+    wl = np.linalg.eigvalsh(G)[::-1]
+    scale = np.abs(wl).max()
+    np.testing.assert_allclose(w, wl, rtol=0, atol=4e-15 * scale * max(m, 4))
+    np.testing.assert_allclose(V.T @ V, np.eye(m), atol=1e-13)
+    np.testing.assert_allclose(G @ V, V * w, atol=1e-13 * scale * max(m, 4))
+    assert np.all(np.diff(w) <= 0) and 0 < int(info.item()) + 1 <= 30
