@@ -83,6 +83,11 @@ int omb_unscale(const double* d_x0, const double* d_cnt, const double* d_scl, in
 int64_t omb_gram_ws_bytes(int64_t F, int64_t n_c, int64_t m);
 int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
              double* d_Gf, void* d_ws, void* stream);
+/* Row means (np.average(x, axis=1), sparse_sensing.py:112, bit-exact) written to d_cnt_out AND the
+ * per-feature Grams of the rows centred by them, from ONE read of X (m <= 64; larger m runs
+ * omb_row_means then omb_gram). */
+int omb_gram_rowmeans(const double* d_X, int64_t F, int64_t n_c, int64_t m, double* d_cnt_out,
+                      double* d_Gf, void* d_ws, void* stream);
 /* G (m x m) = sum_f Gf[f] / scl[f]^2, fixed order. d_scl may be NULL (all ones). */
 int omb_gram_combine(const double* d_Gf, int64_t F, int64_t m, const double* d_scl, double* d_G,
                      void* stream);

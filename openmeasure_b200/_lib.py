@@ -23,6 +23,7 @@ SIGNATURES = {
     "omb_scale_rows": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "omb_unscale": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "omb_gram_ws_bytes": (_i64, [_i64, _i64, _i64]),
+    "omb_gram_rowmeans": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "omb_gram": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "omb_gram_combine": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "omb_eigh_max_m": (_int, []),

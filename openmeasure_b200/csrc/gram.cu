@@ -144,7 +144,7 @@ constexpr int GS_STAGES = 4;
 template <int NB>
 __global__ void __launch_bounds__(GS_THREADS)
 gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double* __restrict__ cnt,
-                  int64_t rows_per_split, int splits, double* __restrict__ part)
+                  double* __restrict__ cnt_out, int64_t rows_per_split, int splits, double* __restrict__ part)
 {
     // ring of GS_STAGES chunks: [GS_CH rows x m] of X followed by the chunk's GS_CH centring values
     extern __shared__ __align__(128) double smem[];
@@ -215,10 +215,33 @@ gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double
             const int64_t k0 = row_lo + (int64_t)ch * GS_CH;
             const int rowc = 4 * warp + fr;                         // row inside the chunk
             const bool rok = (k0 + rowc) < row_hi;
-            const double cv = (rok && cf) ? sC[rowc] : 0.0;
+            double cv = (rok && cf) ? sC[rowc] : 0.0;
             double a[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? sX[rowc * m + 8 * b + fc] - cv : 0.0;
+            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? sX[rowc * m + 8 * b + fc] : 0.0;
+            if (cnt_out) {
+                // np.average(x, axis=1) from the fragments already in registers: lane fc of a row's
+                // 8 lanes holds numpy's accumulator fc (a[0] + a[1] + ... over the full octets), the
+                // shuffles are numpy's ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the m % 8 tail.
+                const int noct = m >> 3, rem = m & 7;
+                double sacc = -0.0, tail = 0.0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (b == 0) { if (noct > 0) sacc = a[0]; }
+                    else if (b < noct) sacc += a[b];
+                    if (b == noct) tail = a[b];
+                }
+                if (noct > 0) {
+                    sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 4);
+                    sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 8);
+                    sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 16);
+                }
+                for (int e = 0; e < rem; ++e) sacc += __shfl_sync(0xFFFFFFFFu, tail, fr + 4 * e);
+                cv = sacc / (double)m;
+                if (fc == 0 && rok) cnt_out[(int64_t)f * n_c + k0 + rowc] = cv;
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? a[b] - cv : 0.0;
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
 #pragma unroll
@@ -254,7 +277,7 @@ static size_t gram_small_smem(int m)
     return sizeof(double) * ((size_t)GS_STAGES * stage_doubles + GT * GT);
 }
 
-typedef void (*GramSmallFn)(const double*, int64_t, int, const double*, int64_t, int, double*);
+typedef void (*GramSmallFn)(const double*, int64_t, int, const double*, double*, int64_t, int, double*);
 static GramSmallFn pick_gram_small(int m)
 {
     switch ((m + 7) / 8) {
@@ -332,8 +355,33 @@ extern "C" int64_t omb_gram_ws_bytes(int64_t F, int64_t n_c, int64_t m)
     return (int64_t)sizeof(double) * F * p.splits * p.ntiles * GT * GT;
 }
 
+namespace omb {
+static int gram_impl(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt, double* d_cnt_out,
+                     double* d_Gf, void* d_ws, void* stream);
+}
+
 extern "C" int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt,
                         double* d_Gf, void* d_ws, void* stream)
+{
+    return gram_impl(d_X, F, n_c, m, d_cnt, nullptr, d_Gf, d_ws, stream);
+}
+
+// Row means AND the centred per-feature Grams from one read of X (m <= 64: the Gram kernel derives
+// np.average(x, axis=1) from the fragments it has in registers); larger m: two kernels.
+extern "C" int omb_gram_rowmeans(const double* d_X, int64_t F, int64_t n_c, int64_t m, double* d_cnt_out,
+                                 double* d_Gf, void* d_ws, void* stream)
+{
+    OMB_CHECK_ARG(d_cnt_out, "null pointer");
+    if (m > 64) {
+        int rc = omb_row_means(d_X, F * n_c, m, d_cnt_out, stream);
+        if (rc) return rc;
+        return gram_impl(d_X, F, n_c, m, d_cnt_out, nullptr, d_Gf, d_ws, stream);
+    }
+    return gram_impl(d_X, F, n_c, m, nullptr, d_cnt_out, d_Gf, d_ws, stream);
+}
+
+int omb::gram_impl(const double* d_X, int64_t F, int64_t n_c, int64_t m, const double* d_cnt, double* d_cnt_out,
+                          double* d_Gf, void* d_ws, void* stream)
 {
     OMB_CHECK_ARG(d_X && d_Gf && d_ws, "null pointer");
     OMB_CHECK_ARG(F > 0 && n_c > 0 && m > 0, "non-positive size");
@@ -347,7 +395,7 @@ extern "C" int omb_gram(const double* d_X, int64_t F, int64_t n_c, int64_t m, co
         GramSmallFn fn = pick_gram_small((int)m);
         const size_t smem = gram_small_smem((int)m);
         OMB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<grid, GS_THREADS, smem, st>>>(d_X, n_c, (int)m, d_cnt, p.rows_per_split, p.splits, (double*)d_ws);
+        fn<<<grid, GS_THREADS, smem, st>>>(d_X, n_c, (int)m, d_cnt, d_cnt_out, p.rows_per_split, p.splits, (double*)d_ws);
         rc = check_launch("gram_small_kernel");
     } else {
         p = gram_plan(F, n_c, m);

@@ -85,8 +85,7 @@ __device__ __forceinline__ bool descend(int64_t& off, int64_t& n, uint32_t path,
 {
     for (int d = depth - 1; d >= 0; --d) {
         if (n <= 128) return (path & ((2u << d) - 1u)) == 0u;
-        int64_t n2 = n / 2;
-        n2 -= n2 % 8;
+        const int64_t n2 = (int64_t)(((uint64_t)n >> 1) & ~(uint64_t)7);      // n/2 rounded down to 8
         if ((path >> d) & 1u) { off += n2; n -= n2; }
         else n = n2;
     }
@@ -117,7 +116,7 @@ row_means_kernel(const double* __restrict__ X, int64_t rows, int64_t m, double* 
 // slots) and writes its value to the level-LT array; a second kernel sweeps the top LT levels.
 // ---------------------------------------------------------------------------------------------
 constexpr int BS_THREADS = 256;
-constexpr int BS_LC_MAX = 6;                 // up to 64 leaves (~6.5K elements) per CTA subtree
+constexpr int BS_LC_MAX = 6;                 // 64 leaves (~7K elements) per CTA subtree: one per quad
 
 struct BlockPlan { int D, LT, LC; };
 
@@ -133,6 +132,63 @@ static BlockPlan make_plan(int64_t n0)
     return p;
 }
 
+// Sum of a leaf (n <= 128) by a QUAD: lane q owns numpy's accumulators 2q and 2q+1 and fetches them
+// with one 128-bit load per octet.  All (<= 16) octet loads are issued before the first add, so a
+// thread keeps up to 256 bytes in flight: the pass is bound by HBM, not by the add chain.
+// Every lane of the quad returns the result.  `vec`: the leaf is 16-byte aligned.
+template <class Map, bool MINMAX>
+__device__ __forceinline__ double leaf_sum_quad(const double* __restrict__ a, int n, int q, unsigned qmask, bool vec,
+                                                Map f, double& lo, double& hi)
+{
+    if (n < 8) {
+        double res = -0.0;
+        for (int i = 0; i < n; ++i) {
+            double x = a[i];
+            if (MINMAX) { lo = fmin(lo, x); hi = fmax(hi, x); }
+            res += f(x);
+        }
+        return res;
+    }
+    const int noct = n >> 3;
+    double2 x[16];
+    const double* p = a + 2 * q;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < noct) x[i] = ldg_stream2(p + 8 * i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < noct) { x[i].x = ldg_stream(p + 8 * i); x[i].y = ldg_stream(p + 8 * i + 1); }
+    }
+    double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < noct) {
+            if (MINMAX) { lo = fmin(lo, fmin(x[i].x, x[i].y)); hi = fmax(hi, fmax(x[i].x, x[i].y)); }
+            if (i == 0) { r0 = f(x[i].x); r1 = f(x[i].y); }
+            else { r0 += f(x[i].x); r1 += f(x[i].y); }
+        }
+    }
+    double r = r0 + r1;                       // (r0+r1), (r2+r3), (r4+r5), (r6+r7)
+    r += __shfl_xor_sync(qmask, r, 1);
+    r += __shfl_xor_sync(qmask, r, 2);
+    for (int i = noct * 8; i < n; ++i) {
+        double xx = a[i];
+        if (MINMAX) { lo = fmin(lo, xx); hi = fmax(hi, xx); }
+        r += f(xx);
+    }
+    return r;
+}
+
+// one up-sweep level by shuffles: slot `sl` (a multiple of 2*half) absorbs slot sl+half if present
+__device__ __forceinline__ double upsweep_level(double v, int sl, int half, int lane_stride, unsigned present_bits)
+{
+    const double pv = __shfl_xor_sync(0xFFFFFFFFu, v, half * lane_stride);
+    if ((sl & (2 * half - 1)) == 0 && ((present_bits >> (sl + half)) & 1u)) v = v + pv;
+    return v;
+}
+
 template <int MODE>   // 0: sum/min/max   1: sum of squared deviations about stats[f*4]/count
 __global__ void __launch_bounds__(BS_THREADS)
 block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LT, int LC,
@@ -140,17 +196,18 @@ block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LT, int
                   unsigned char* __restrict__ top_flag, double* __restrict__ top_min,
                   double* __restrict__ top_max)
 {
-    __shared__ double s_val[1 << BS_LC_MAX];
-    __shared__ unsigned char s_flag[1 << BS_LC_MAX];
+    __shared__ double s_val[BS_THREADS / 32];
+    __shared__ unsigned s_flag[BS_THREADS / 32];
     __shared__ double s_lo[BS_THREADS / 32], s_hi[BS_THREADS / 32];
 
     const int f = blockIdx.y;
     const int64_t ntop = (int64_t)1 << LT;
     const double* base = X + (int64_t)f * block_elems;
-    const int l8 = threadIdx.x & 7;
-    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
-    const int grp = threadIdx.x >> 3;
-    constexpr int NGRP = BS_THREADS / 8;
+    const bool vec = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane & 3;
+    const unsigned qmask = 0xFu << (lane & 28);
+    const int slot = threadIdx.x >> 2;            // one quad per leaf slot
     const int nslots = 1 << LC;
     double mu = 0.0;
     if (MODE == 1) mu = stats[f * 4 + 0] / mean_count;
@@ -159,42 +216,52 @@ block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LT, int
         int64_t off = 0, n = block_elems;
         const bool present = descend(off, n, (uint32_t)node, LT);
         double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
-        if (present) {
-            for (int slot = grp; slot < nslots; slot += NGRP) {
-                int64_t o2 = off, n2 = n;
-                bool here = descend(o2, n2, (uint32_t)slot, LC);
-                double v = 0.0;
-                if (here) {
-                    if (MODE == 0) v = leaf_sum<MapId, true>(base + o2, n2, l8, gmask, MapId(), lo, hi);
-                    else { MapSqDev mp; mp.mu = mu; v = leaf_sum<MapSqDev, false>(base + o2, n2, l8, gmask, mp, lo, hi); }
-                }
-                if (l8 == 0) { s_val[slot] = v; s_flag[slot] = here ? 1 : 0; }
+        double v = 0.0;
+        bool here = false;
+        if (present && slot < nslots) {
+            int64_t o2 = off, n2 = n;
+            here = descend(o2, n2, (uint32_t)slot, LC);
+            if (here) {
+                if (MODE == 0) v = leaf_sum_quad<MapId, true>(base + o2, (int)n2, q, qmask, vec, MapId(), lo, hi);
+                else { MapSqDev mp; mp.mu = mu; v = leaf_sum_quad<MapSqDev, false>(base + o2, (int)n2, q, qmask, vec, mp, lo, hi); }
             }
         }
-        __syncthreads();
-        if (present) {
-            // up-sweep: a node's value ends in its left-most descendant slot
-            for (int half = 1; half < nslots; half <<= 1) {
-                int idx = threadIdx.x * 2 * half;
-                if (idx + half < nslots && s_flag[idx + half]) s_val[idx] = s_val[idx] + s_val[idx + half];
-                __syncthreads();
-            }
-        }
+        // up-sweep inside the warp (8 slots, one per quad): a node's value ends in its left-most slot
+        const unsigned hb = __ballot_sync(0xFFFFFFFFu, here);
+        unsigned pres = 0;                         // bit s: slot s of this warp is present
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) pres |= ((hb >> (4 * sidx)) & 1u) << sidx;
+        const int sl = lane >> 2;
+        v = upsweep_level(v, sl, 1, 4, pres);
+        v = upsweep_level(v, sl, 2, 4, pres);
+        v = upsweep_level(v, sl, 4, 4, pres);
         if (MODE == 0) {
             for (int o = 16; o > 0; o >>= 1) {
                 lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
                 hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
             }
-            if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
-            __syncthreads();
         }
-        if (threadIdx.x == 0) {
-            top_val[(int64_t)f * ntop + node] = present ? s_val[0] : 0.0;
-            top_flag[(int64_t)f * ntop + node] = present ? 1 : 0;
-            if (MODE == 0) {
-                for (int w = 1; w < BS_THREADS / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
-                top_min[(int64_t)f * ntop + node] = lo;
-                top_max[(int64_t)f * ntop + node] = hi;
+        if (lane == 0) { s_val[warp] = v; s_flag[warp] = pres & 1u; if (MODE == 0) { s_lo[warp] = lo; s_hi[warp] = hi; } }
+        __syncthreads();
+        if (warp == 0) {
+            // the 8 warp subtrees (slots 8w .. 8w+7): three more levels
+            const int w = lane & 7;
+            double vv = s_val[w];
+            unsigned wp = 0;
+#pragma unroll
+            for (int k = 0; k < BS_THREADS / 32; ++k) wp |= (s_flag[k] & 1u) << k;
+            vv = upsweep_level(vv, w, 1, 1, wp);
+            vv = upsweep_level(vv, w, 2, 1, wp);
+            vv = upsweep_level(vv, w, 4, 1, wp);
+            if (lane == 0) {
+                top_val[(int64_t)f * ntop + node] = present ? vv : 0.0;
+                top_flag[(int64_t)f * ntop + node] = present ? 1 : 0;
+                if (MODE == 0) {
+                    double l2 = s_lo[0], h2 = s_hi[0];
+                    for (int k = 1; k < BS_THREADS / 32; ++k) { l2 = fmin(l2, s_lo[k]); h2 = fmax(h2, s_hi[k]); }
+                    top_min[(int64_t)f * ntop + node] = l2;
+                    top_max[(int64_t)f * ntop + node] = h2;
+                }
             }
         }
         __syncthreads();
@@ -362,9 +429,8 @@ extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems
     double* top_min = top_val + F * ntop;
     double* top_max = top_min + F * ntop;
     unsigned char* top_flag = (unsigned char*)(top_max + F * ntop);
-    int64_t gx = ntop;
-    int64_t cap = (int64_t)sm_count() * 16;
-    if (gx > cap) gx = cap;
+    int64_t gx = ntop;                       // one ~30-60 KB node per CTA
+    if (gx > 65535 * 16) gx = 65535 * 16;
     dim3 grid((unsigned)gx, (unsigned)F);
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0)

@@ -79,7 +79,8 @@ class Engine:
         self.layout = _comm.ShardLayout(self.F, cells, self.rank)
         self.n_c = self.layout.n_c                      # global cells per feature
         self.cell0 = self.layout.cell0
-        self.cnt = None
+        self._cnt = None
+        self._cnt_pending = False                        # row means still to be produced by the Gram pass
         self.scl = None
         self.Ut = None
         self.vn = None
@@ -92,12 +93,25 @@ class Engine:
         if st is not None and st[0][st[1]:st[1] + 1].view(torch.int64).item() != 0:
             raise _lib.OmbError("multi-rank placement: a peer rank did not publish its record (10 s timeout)")
 
+    @property
+    def cnt(self):
+        """Centring value per local row; flushes row means deferred to the Gram pass."""
+        if self._cnt_pending:
+            _lib.call("omb_row_means", _p(self.X), self.n_loc, self.m, _p(self._cnt), _stream())
+            self._cnt_pending = False
+        return self._cnt
+
+    @cnt.setter
+    def cnt(self, v):
+        self._cnt, self._cnt_pending = v, False
+
     def _shard_args(self):
         return (self.n_c_loc, self.n_c, self.cell0, self.rank, self.world)
 
     # ------------------------------------------------------------------------------------ K1
-    def stats(self, scale_type="std", axis_cnt=1):
-        """Centring vector and per-feature scale (sparse_sensing.py:106-167)."""
+    def stats(self, scale_type="std", axis_cnt=1, defer_row_means=False):
+        """Centring vector and per-feature scale (sparse_sensing.py:106-167).  defer_row_means: the
+        caller runs gram() next, whose single read of X also yields the row means (m <= 64)."""
         if scale_type not in SCALE_CODES:
             raise NotImplementedError("The scaling method selected has not been implemented yet")
         F, ncl, m = self.F, self.n_c_loc, self.m
@@ -106,8 +120,12 @@ class Engine:
         stats = torch.zeros(F * 4, dtype=torch.float64, device=self.dev)
         blk = ncl * m
         ws = _ws(_lib.load().omb_block_stats_ws_bytes(F, blk), self.dev)
+        pending = False
         if axis_cnt == 1:
-            _lib.call("omb_row_means", _p(self.X), self.n_loc, m, _p(cnt), st)
+            if defer_row_means:
+                pending = True
+            else:
+                _lib.call("omb_row_means", _p(self.X), self.n_loc, m, _p(cnt), st)
         count = self.n_c * m
         _lib.call("omb_block_stats", _p(self.X), F, blk, 0, count, _p(stats), _p(ws), st)
         if self.world > 1:
@@ -120,6 +138,7 @@ class Engine:
         _lib.call("omb_finalize_scale", _p(stats), F, count, SCALE_CODES[scale_type], _p(scl),
                   1 if axis_cnt is None else 0, _p(cnt), ncl, st)
         self.cnt, self.scl, self.block_stats = cnt, scl, stats
+        self._cnt_pending = pending
         return cnt, scl
 
     def set_scale_feature(self, f, value):
@@ -132,7 +151,11 @@ class Engine:
         st = _stream()
         Gf = torch.empty(F * m * m, dtype=torch.float64, device=self.dev)
         ws = _ws(_lib.load().omb_gram_ws_bytes(F, ncl, m), self.dev)
-        _lib.call("omb_gram", _p(self.X), F, ncl, m, _p(self.cnt if centred else None), _p(Gf), _p(ws), st)
+        if centred and self._cnt_pending:               # row means + centred Grams from one read of X
+            _lib.call("omb_gram_rowmeans", _p(self.X), F, ncl, m, _p(self._cnt), _p(Gf), _p(ws), st)
+            self._cnt_pending = False
+        else:
+            _lib.call("omb_gram", _p(self.X), F, ncl, m, _p(self.cnt if centred else None), _p(Gf), _p(ws), st)
         G = torch.empty(m, m, dtype=torch.float64, device=self.dev)
         _lib.call("omb_gram_combine", _p(Gf), F, m, _p(self.scl if scaled else None), _p(G), st)
         if self.world > 1:                          # fixed order: identical bits on every rank

@@ -193,20 +193,20 @@ class ROM:
         self._scale_stats(scale_type, axis_cnt)
         return self.X0
 
-    def _scale_stats(self, scale_type, axis_cnt):
+    def _scale_stats(self, scale_type, axis_cnt, defer_row_means=False):
         if scale_type in _BROKEN_SCALES or axis_cnt not in (1, None):
             raise ValueError('could not broadcast the centring/scaling coefficient '
                              '(same failure as the reference for this option)')
         eng = self._engine()
         if scale_type == 'median':
-            eng.stats('none', axis_cnt)
+            eng.stats('none', axis_cnt, defer_row_means)
             blocks = eng.X.view(eng.F, -1)
             k = blocks.shape[1]
             lo = torch.kthvalue(blocks, (k + 1) // 2, dim=1).values
             hi = torch.kthvalue(blocks, k // 2 + 1, dim=1).values
             eng.scl = ((lo + hi) / 2).contiguous()       # np.median (:140)
         else:
-            eng.stats(scale_type, axis_cnt)
+            eng.stats(scale_type, axis_cnt, defer_row_means)
         for k in ("X_cnt", "X_scl", "X0"):
             self._host.pop(k, None)
 
@@ -308,7 +308,7 @@ class ROM:
         if basis is None:
             self._validate_modes(select_modes, n_modes)
         self.scale_type = scale_type
-        self._scale_stats(scale_type, axis_cnt)
+        self._scale_stats(scale_type, axis_cnt, defer_row_means=basis is None)
         eng = self._engine()
         if basis is None:
             Ar, _ = self._pod(eng, select_modes, n_modes, centred=True, scaled=True)
