@@ -148,7 +148,7 @@ static int launch_bp(const double* X, int64_t n, int64_t n_c, int m, const doubl
 constexpr int BS_THREADS2 = 256;
 
 template <int QB>
-__global__ void __launch_bounds__(BS_THREADS2)
+__global__ void __launch_bounds__(BS_THREADS2, 2)
 backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, const double* __restrict__ cnt,
                          const double* __restrict__ scl, const double* __restrict__ W, int r,
                          double* __restrict__ Ut, double* __restrict__ vn)

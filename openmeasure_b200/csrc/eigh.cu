@@ -3,7 +3,7 @@
 // Replaces the bidiagonal divide-and-conquer on R inside LAPACK dgesdd (np.linalg.svd, reference
 // sparse_sensing.py:272).  One CTA, matrix and eigenvectors in shared memory, cyclic two-sided
 // Jacobi with the round-robin parallel ordering (M/2 disjoint rotations per step, M-1 steps per
-// sweep).  For an m = 41 Gram this takes ~0.2 ms, where a library syevd spends ~0.9 ms mostly in
+// sweep).  A library syevd spends ~0.9 ms on an m = 41 Gram, mostly in
 // host synchronisation; Jacobi also resolves the small eigenvalues of a positive semi-definite
 // matrix to high relative accuracy.  Output: eigenvalues in DESCENDING order, V[i][k] = component
 // i of eigenvector k.
@@ -14,19 +14,58 @@ namespace omb {
 
 constexpr int EJ_MAX = 64;
 constexpr int EJ_LD = EJ_MAX + 1;
-constexpr int EJ_THREADS = 512;
+constexpr int EJ_THREADS = 1024;
 constexpr int EJ_MAX_SWEEPS = 30;
 
+// Jacobi rotation for the pivot a_pq.  Any exactly orthogonal (c, s) is a valid similarity; how well
+// it annihilates a_pq only sets the convergence rate.  FP64 sqrt/div/rsqrt are ~50-instruction
+// dependent chains (this step is pure latency: one warp, 21 lanes), so the angle is found in FP32
+// on power-of-two-scaled inputs (relative error ~1e-7: a_pq shrinks by that factor instead of to
+// zero, which leaves the quadratic convergence intact) and only the normalisation is done in FP64,
+// in the rational (half-angle) form  c = (1 - u)/(1 + u), s = 2 tau/(1 + u), u = tau^2, which is
+// orthogonal to rounding for ANY tau; 1/(1 + u) is an FP32 seed plus two Newton steps.
+// `big`: the rotation can still move an eigenvalue at the 1e-16 * lambda_max level.
+__device__ __forceinline__ void jacobi_rot(double apq, double app, double aqq, double floor_abs, double big_abs,
+                                           double& c, double& s, bool& big)
+{
+    c = 1.0; s = 0.0; big = false;
+    const double rel2 = apq * apq, den = fabs(app * aqq);
+    // rotate unless |apq| <= eps * sqrt(app * aqq) (compared squared) or below the floor
+    if (!(rel2 > 1.2325951644078309e-32 * den && fabs(apq) > floor_abs)) return;
+    const double d = aqq - app, b = 2.0 * apq;
+    const double ad = fabs(d), ab = fabs(b);
+    const double mx = ad > ab ? ad : ab;
+    int e = (int)((__double_as_longlong(mx) >> 52) & 0x7FF);
+    e = e < 1 ? 1 : (e > 2045 ? 2045 : e);
+    const double sc = __longlong_as_double((long long)(2046 - e) << 52);      // 2^(1023 - e): max(|d|,|b|) -> [1, 2)
+    const float df = (float)(d * sc), bf = (float)(b * sc);
+    const float hf = sqrtf(fmaf(df, df, bf * bf));
+    const float tf = __fdividef(bf, df + copysignf(hf, df));                 // tan(theta), |theta| <= pi/4
+    // (|b| < 1e-38 |d| underflows to tf = 0: such a rotation is the identity to FP64 rounding anyway)
+    const double tau = (double)__fdividef(tf, 1.0f + sqrtf(fmaf(tf, tf, 1.0f)));   // tan(theta / 2)
+    const double u = tau * tau, w = 1.0 + u;
+    double y = (double)__frcp_rn((float)w);
+    double r1 = fma(-w, y, 1.0);
+    y = fma(y, r1, y);
+    r1 = fma(-w, y, 1.0);
+    y = fma(y, r1, y);
+    c = (1.0 - u) * y;
+    s = (tau + tau) * y;
+    big = rel2 > 1.0e-18 * den && fabs(apq) > big_abs;
+}
+
+// Two barriers per step: (1) lanes 0..npair-1 of warp 0 compute the step's rotations, (2) every
+// thread applies them to its fixed work items (no index arithmetic inside the sweeps):
+//   e <  npair^2 : block (pair i rows) x (pair j columns) of  A <- J^T A J
+//   e >= npair^2 : two rows of  V <- V J  for one pair
 __global__ void __launch_bounds__(EJ_THREADS)
 eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_out, double* __restrict__ V_out,
                    int* __restrict__ info)
 {
     extern __shared__ double sm[];
-    double* A = sm;                         // [EJ_MAX][EJ_LD]
-    double* V = sm + EJ_MAX * EJ_LD;        // [EJ_MAX][EJ_LD]
+    double* A = sm;                           // [EJ_MAX][EJ_LD]
+    double* V = sm + EJ_MAX * EJ_LD;          // [EJ_MAX][EJ_LD]
     __shared__ double s_c[EJ_MAX / 2], s_s[EJ_MAX / 2];
-    __shared__ int s_p[EJ_MAX / 2], s_q[EJ_MAX / 2];
-    __shared__ int s_rot;                   // rotations applied in the current sweep
     __shared__ int s_order[EJ_MAX];
     __shared__ unsigned short s_sched[(EJ_MAX - 1) * (EJ_MAX / 2)];
 
@@ -51,9 +90,6 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
         for (int i = 0; i < m; ++i) dmax = fmax(dmax, fabs(A[i * EJ_LD + i]));
         s_floor = dmax * 1.0e-20;
     }
-    __syncthreads();
-    const double floor_abs = s_floor, big_abs = s_floor * 1.0e7;      // 1e-13 * max|a_ii|
-
     // round-robin schedule: pair i of step k, stored once (no integer division in the sweeps)
     for (int e = threadIdx.x; e < (M - 1) * npair; e += EJ_THREADS) {
         const int step = e / npair, i = e - step * npair;
@@ -64,47 +100,44 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
         s_sched[e] = (unsigned short)((p << 8) | q);
     }
     __syncthreads();
+    const double floor_abs = s_floor, big_abs = s_floor * 1.0e7;      // 1e-13 * max|a_ii|
+
+    // fixed work items of this thread (at most two: 2 * npair^2 <= 2048 items, 1024 threads)
+    const int nblk = npair * npair, nitem = 2 * nblk;
+    int it_i[2], it_j[2];                    // A item: (i, j);  V item: (npair + pair i, row pair j)
+    for (int k = 0; k < 2; ++k) {
+        const int e = threadIdx.x + k * EJ_THREADS;
+        it_i[k] = it_j[k] = -1;
+        if (e < nblk) { it_i[k] = e / npair; it_j[k] = e - it_i[k] * npair; }
+        else if (e < nitem) { const int u = e - nblk; it_j[k] = u / npair; it_i[k] = npair + (u - it_j[k] * npair); }
+    }
 
     int sweep = 0;
     for (; sweep < EJ_MAX_SWEEPS; ++sweep) {
-        if (threadIdx.x == 0) s_rot = 0;
-        __syncthreads();
+        int sweep_big = 0;
         for (int step = 0; step < M - 1; ++step) {
+            const unsigned short* sched = s_sched + step * npair;
+            int my_big = 0;
             // 1. the M/2 disjoint pairs of this step and their rotations
             if (threadIdx.x < npair) {
-                const int i = threadIdx.x;
-                const unsigned short pq = s_sched[step * npair + i];
-                const int p = pq >> 8, q = pq & 255;
+                const int p = sched[threadIdx.x] >> 8, q = sched[threadIdx.x] & 255;
                 double c = 1.0, s = 0.0;
-                if (q < m) {
-                    const double apq = A[p * EJ_LD + q];
-                    const double app = A[p * EJ_LD + p], aqq = A[q * EJ_LD + q];
-                    const double rel2 = apq * apq, den = fabs(app * aqq);
-                    // rotate unless |apq| <= eps * sqrt(app * aqq) (compared squared) or below the floor
-                    if (rel2 > 1.2325951644078309e-32 * den && fabs(apq) > floor_abs) {
-                        // t = tan(theta) of the smaller root: b / (d + sign(d) * hypot(d, b))
-                        const double d = aqq - app, b = 2.0 * apq;
-                        const double h = sqrt(fma(d, d, b * b));
-                        const double t = b / (d + copysign(h, d));
-                        c = rsqrt(fma(t, t, 1.0));
-                        s = t * c;
-                        // "big" rotation: convergence is quadratic, so a sweep without any of these
-                        // is the last one that can change an eigenvalue at the 1e-16 * lambda_max level
-                        if (rel2 > 1.0e-18 * den && fabs(apq) > big_abs) atomicAdd(&s_rot, 1);
-                    }
-                }
-                s_p[i] = p; s_q[i] = q; s_c[i] = c; s_s[i] = s;
+                bool big = false;
+                if (q < m) jacobi_rot(A[p * EJ_LD + q], A[p * EJ_LD + p], A[q * EJ_LD + q], floor_abs, big_abs, c, s, big);
+                s_c[threadIdx.x] = c; s_s[threadIdx.x] = s;
+                my_big = big ? 1 : 0;
             }
             __syncthreads();
-            // 2. A <- J^T A J by 2 x 2 blocks (pair i rows x pair j columns), V <- V J by column pairs
-            const int nblk = npair * npair;
-            for (int e = threadIdx.x; e < nblk + npair * m; e += EJ_THREADS) {
-                if (e < nblk) {
-                    const int i = e / npair, j = e - i * npair;
+            // 2. A <- J^T A J by 2 x 2 blocks, V <- V J by column pairs (every entry has one owner)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (it_i[k] < 0) continue;
+                if (it_i[k] < npair) {
+                    const int i = it_i[k], j = it_j[k];
                     const double si = s_s[i], sj = s_s[j];
                     if (si == 0.0 && sj == 0.0) continue;
-                    const int pi = s_p[i], qi = s_q[i], pj = s_p[j], qj = s_q[j];
                     const double ci = s_c[i], cj = s_c[j];
+                    const int pi = sched[i] >> 8, qi = sched[i] & 255, pj = sched[j] >> 8, qj = sched[j] & 255;
                     const double a00 = A[pi * EJ_LD + pj], a01 = A[pi * EJ_LD + qj];
                     const double a10 = A[qi * EJ_LD + pj], a11 = A[qi * EJ_LD + qj];
                     // columns (J_j), then rows (J_i^T)
@@ -115,23 +148,26 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
                     A[qi * EJ_LD + pj] = si * b00 + ci * b10;
                     A[qi * EJ_LD + qj] = si * b01 + ci * b11;
                 } else {
-                    const int e2 = e - nblk;
-                    const int i = e2 / m, row = e2 - i * m;
+                    const int i = it_i[k] - npair, r0 = 2 * it_j[k];
                     const double s = s_s[i];
                     if (s != 0.0) {
-                        const int p = s_p[i], q = s_q[i];
                         const double c = s_c[i];
-                        const double vp = V[row * EJ_LD + p], vq = V[row * EJ_LD + q];
-                        V[row * EJ_LD + p] = c * vp - s * vq;
-                        V[row * EJ_LD + q] = s * vp + c * vq;
+                        const int p = sched[i] >> 8, q = sched[i] & 255;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int row = r0 + rr;
+                            const double vp = V[row * EJ_LD + p], vq = V[row * EJ_LD + q];
+                            V[row * EJ_LD + p] = c * vp - s * vq;
+                            V[row * EJ_LD + q] = s * vp + c * vq;
+                        }
                     }
                 }
             }
-            __syncthreads();
+            sweep_big |= __syncthreads_or(my_big);
         }
-        if (s_rot == 0) break;
-        __syncthreads();
+        if (!sweep_big) break;
     }
+
 
     // descending order by rank counting (ties broken by index)
     if (threadIdx.x < m) {

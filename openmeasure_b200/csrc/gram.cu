@@ -207,42 +207,53 @@ gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double
 #pragma unroll
         for (int b = 0; b < NB; ++b) colok[b] = (8 * b + fc) < m;
 
+        const int rowc = 4 * warp + fr;                             // this lane's row inside every chunk
+        const int noct = m >> 3, rem = m & 7;
+        const double dm = (double)m;
+        const int64_t myrow0 = row_lo + rowc;
+        double* cnt_dst = cnt_out ? cnt_out + (int64_t)f * n_c + myrow0 : nullptr;
         for (int ch = 0; ch < nchunks; ++ch) {
             const int s = ch % GS_STAGES;
             mbar_wait(&full_bar[s], (ch / GS_STAGES) & 1);
             const double* sX = smem + s * stage_doubles;
             const double* sC = sX + ((GS_CH * m + 1) & ~1);
-            const int64_t k0 = row_lo + (int64_t)ch * GS_CH;
-            const int rowc = 4 * warp + fr;                         // row inside the chunk
-            const bool rok = (k0 + rowc) < row_hi;
-            double cv = (rok && cf) ? sC[rowc] : 0.0;
+            const bool rok = (myrow0 + (int64_t)ch * GS_CH) < row_hi;
+            // unconditional loads (columns >= m read the next row / the slack behind the ring: always
+            // inside shared memory), masked afterwards: no branches in the chunk loop
+            const double* px = sX + rowc * m + fc;
             double a[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? sX[rowc * m + 8 * b + fc] : 0.0;
+            for (int b = 0; b < NB; ++b) a[b] = px[8 * b];
+            double cv = cf ? sC[rowc] : 0.0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? a[b] : 0.0;
             if (cnt_out) {
                 // np.average(x, axis=1) from the fragments already in registers: lane fc of a row's
                 // 8 lanes holds numpy's accumulator fc (a[0] + a[1] + ... over the full octets), the
                 // shuffles are numpy's ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the m % 8 tail.
-                const int noct = m >> 3, rem = m & 7;
                 double sacc = -0.0, tail = 0.0;
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    if (b == 0) { if (noct > 0) sacc = a[0]; }
-                    else if (b < noct) sacc += a[b];
-                    if (b == noct) tail = a[b];
+                    if (b == 0) sacc = noct > 0 ? a[0] : sacc;
+                    else sacc = b < noct ? sacc + a[b] : sacc;
+                    tail = b == noct ? a[b] : tail;
                 }
                 if (noct > 0) {
                     sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 4);
                     sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 8);
                     sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 16);
                 }
-                for (int e = 0; e < rem; ++e) sacc += __shfl_sync(0xFFFFFFFFu, tail, fr + 4 * e);
-                cv = sacc / (double)m;
-                if (fc == 0 && rok) cnt_out[(int64_t)f * n_c + k0 + rowc] = cv;
+#pragma unroll
+                for (int e = 0; e < 7; ++e) {
+                    const double tv = __shfl_sync(0xFFFFFFFFu, tail, fr + 4 * e);
+                    sacc = e < rem ? sacc + tv : sacc;
+                }
+                cv = sacc / dm;
+                if (fc == 0 && rok) cnt_dst[(int64_t)ch * GS_CH] = cv;
             }
 #pragma unroll
             for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? a[b] - cv : 0.0;
-            __syncwarp();
+            __syncwarp();                                          // every lane holds its (used) values
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
 #pragma unroll
             for (int bi = 0; bi < NB; ++bi)
@@ -298,7 +309,9 @@ static GramPlan gram_small_plan(int64_t F, int64_t n_c)
     GramPlan p;
     p.T = 1;
     p.ntiles = 1;
-    int64_t splits = ceil_div((int64_t)sm_count() * 2, F);
+    // one CTA per SM fits (registers): a single full wave, never a straggler CTA
+    int64_t splits = (int64_t)sm_count() / F;
+    if (splits < 1) splits = 1;
     const int64_t unit = GS_CH;                                 // rows per chunk
     int64_t max_splits = ceil_div(n_c, 4 * unit);
     if (splits > max_splits) splits = max_splits;

@@ -115,21 +115,55 @@ row_means_kernel(const double* __restrict__ X, int64_t rows, int64_t m, double* 
 // block tree sum.  Tree depth D = LT + LC: a CTA evaluates one depth-LT node (a subtree of 2^LC
 // slots) and writes its value to the level-LT array; a second kernel sweeps the top LT levels.
 // ---------------------------------------------------------------------------------------------
-constexpr int BS_THREADS = 256;
-constexpr int BS_LC_MAX = 6;                 // 64 leaves (~7K elements) per CTA subtree: one per quad
+constexpr int BS_THREADS = 128;               // 4 independent warps: no CTA barrier in the sweep
+constexpr int BS_CTAS_PER_SM = 5;
+constexpr int BS_GX_MAX = 4096;               // CTAs per feature (bounds the min/max partial arrays)
 
-struct BlockPlan { int D, LT, LC; };
+// Tree depth D = LW + LQ: a WARP evaluates one depth-LW node (a subtree of 2^LQ <= 8 leaf slots, one
+// per quad) and writes its value to the level-LW array; a second kernel sweeps the top LW levels.
+struct BlockPlan { int D, LW, LQ; };
 
+// Exact depth of numpy's tree over n0 elements: the distinct range sizes of each level are few, so
+// the levels are walked as small sets until every range is a leaf (<= 128 elements).
 static BlockPlan make_plan(int64_t n0)
 {
-    int D = 0;
-    // all leaves are at depth <= D once n0 / 2^D + 15 <= 128
-    while ((double)n0 / (double)(1ull << D) + 15.0 > 128.0) ++D;
+    int64_t cur[256], nxt[256];
+    int nc = 1, D = 0;
+    cur[0] = n0;
+    for (;;) {
+        int nn = 0;
+        bool split = false;
+        for (int i = 0; i < nc; ++i) {
+            const int64_t n = cur[i];
+            if (n <= 128) continue;
+            split = true;
+            const int64_t n2 = (n / 2) & ~(int64_t)7;
+            const int64_t kids[2] = {n2, n - n2};
+            for (int k = 0; k < 2; ++k) {
+                bool seen = false;
+                for (int j = 0; j < nn; ++j) seen |= (nxt[j] == kids[k]);
+                if (!seen && nn < 256) nxt[nn++] = kids[k];
+            }
+        }
+        if (!split) break;
+        ++D;
+        nc = nn;
+        for (int i = 0; i < nn; ++i) cur[i] = nxt[i];
+    }
     BlockPlan p;
     p.D = D;
-    p.LC = D < BS_LC_MAX ? D : BS_LC_MAX;
-    p.LT = D - p.LC;
+    p.LQ = D < 3 ? D : 3;
+    p.LW = D - p.LQ;
     return p;
+}
+
+// Running min/max by compare-select (one DSETP + selects; fmin/fmax cost ~10 instructions each in
+// FP64 because of their NaN rules).  A NaN never wins a comparison; the block SUM still turns NaN,
+// and block_top_kernel restores numpy's NaN result for min/max from it.
+__device__ __forceinline__ void track_minmax(double x, double& lo, double& hi)
+{
+    lo = (x < lo) ? x : lo;
+    hi = (x > hi) ? x : hi;
 }
 
 // Sum of a leaf (n <= 128) by a QUAD: lane q owns numpy's accumulators 2q and 2q+1 and fetches them
@@ -144,7 +178,7 @@ __device__ __forceinline__ double leaf_sum_quad(const double* __restrict__ a, in
         double res = -0.0;
         for (int i = 0; i < n; ++i) {
             double x = a[i];
-            if (MINMAX) { lo = fmin(lo, x); hi = fmax(hi, x); }
+            if (MINMAX) track_minmax(x, lo, hi);
             res += f(x);
         }
         return res;
@@ -165,7 +199,7 @@ __device__ __forceinline__ double leaf_sum_quad(const double* __restrict__ a, in
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         if (i < noct) {
-            if (MINMAX) { lo = fmin(lo, fmin(x[i].x, x[i].y)); hi = fmax(hi, fmax(x[i].x, x[i].y)); }
+            if (MINMAX) { track_minmax(x[i].x, lo, hi); track_minmax(x[i].y, lo, hi); }
             if (i == 0) { r0 = f(x[i].x); r1 = f(x[i].y); }
             else { r0 += f(x[i].x); r1 += f(x[i].y); }
         }
@@ -175,7 +209,7 @@ __device__ __forceinline__ double leaf_sum_quad(const double* __restrict__ a, in
     r += __shfl_xor_sync(qmask, r, 2);
     for (int i = noct * 8; i < n; ++i) {
         double xx = a[i];
-        if (MINMAX) { lo = fmin(lo, xx); hi = fmax(hi, xx); }
+        if (MINMAX) track_minmax(xx, lo, hi);
         r += f(xx);
     }
     return r;
@@ -190,81 +224,63 @@ __device__ __forceinline__ double upsweep_level(double v, int sl, int half, int 
 }
 
 template <int MODE>   // 0: sum/min/max   1: sum of squared deviations about stats[f*4]/count
-__global__ void __launch_bounds__(BS_THREADS)
-block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LT, int LC,
+__global__ void __launch_bounds__(BS_THREADS, BS_CTAS_PER_SM)
+block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LW, int LQ,
                   const double* __restrict__ stats, double mean_count, double* __restrict__ top_val,
-                  unsigned char* __restrict__ top_flag, double* __restrict__ top_min,
-                  double* __restrict__ top_max)
+                  unsigned char* __restrict__ top_flag, double* __restrict__ cta_min,
+                  double* __restrict__ cta_max)
 {
-    __shared__ double s_val[BS_THREADS / 32];
-    __shared__ unsigned s_flag[BS_THREADS / 32];
-    __shared__ double s_lo[BS_THREADS / 32], s_hi[BS_THREADS / 32];
-
     const int f = blockIdx.y;
-    const int64_t ntop = (int64_t)1 << LT;
+    const int64_t nwn = (int64_t)1 << LW;
     const double* base = X + (int64_t)f * block_elems;
     const bool vec = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = lane & 3;
+    const int q = lane & 3, sl = lane >> 2;       // one quad per leaf slot of the warp's node
     const unsigned qmask = 0xFu << (lane & 28);
-    const int slot = threadIdx.x >> 2;            // one quad per leaf slot
-    const int nslots = 1 << LC;
+    const int nslots = 1 << LQ;
     double mu = 0.0;
     if (MODE == 1) mu = stats[f * 4 + 0] / mean_count;
+    double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
 
-    for (int64_t node = blockIdx.x; node < ntop; node += gridDim.x) {
+    const int64_t nwarps = (int64_t)gridDim.x * (BS_THREADS / 32);
+    for (int64_t wn = (int64_t)blockIdx.x * (BS_THREADS / 32) + warp; wn < nwn; wn += nwarps) {
         int64_t off = 0, n = block_elems;
-        const bool present = descend(off, n, (uint32_t)node, LT);
-        double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
+        const bool present = descend(off, n, (uint32_t)wn, LW);
         double v = 0.0;
         bool here = false;
-        if (present && slot < nslots) {
-            int64_t o2 = off, n2 = n;
-            here = descend(o2, n2, (uint32_t)slot, LC);
+        if (present && sl < nslots) {
+            here = descend(off, n, (uint32_t)sl, LQ);
             if (here) {
-                if (MODE == 0) v = leaf_sum_quad<MapId, true>(base + o2, (int)n2, q, qmask, vec, MapId(), lo, hi);
-                else { MapSqDev mp; mp.mu = mu; v = leaf_sum_quad<MapSqDev, false>(base + o2, (int)n2, q, qmask, vec, mp, lo, hi); }
+                if (MODE == 0) v = leaf_sum_quad<MapId, true>(base + off, (int)n, q, qmask, vec, MapId(), lo, hi);
+                else { MapSqDev mp; mp.mu = mu; v = leaf_sum_quad<MapSqDev, false>(base + off, (int)n, q, qmask, vec, mp, lo, hi); }
             }
         }
-        // up-sweep inside the warp (8 slots, one per quad): a node's value ends in its left-most slot
+        // up-sweep inside the warp: a node's value ends in its left-most slot
         const unsigned hb = __ballot_sync(0xFFFFFFFFu, here);
-        unsigned pres = 0;                         // bit s: slot s of this warp is present
+        unsigned pres = 0;                         // bit s: slot s of this warp's node is present
 #pragma unroll
         for (int sidx = 0; sidx < 8; ++sidx) pres |= ((hb >> (4 * sidx)) & 1u) << sidx;
-        const int sl = lane >> 2;
         v = upsweep_level(v, sl, 1, 4, pres);
         v = upsweep_level(v, sl, 2, 4, pres);
         v = upsweep_level(v, sl, 4, 4, pres);
-        if (MODE == 0) {
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
-                hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
-            }
+        if (lane == 0) {
+            top_val[(int64_t)f * nwn + wn] = present ? v : 0.0;
+            top_flag[(int64_t)f * nwn + wn] = present ? 1 : 0;
         }
-        if (lane == 0) { s_val[warp] = v; s_flag[warp] = pres & 1u; if (MODE == 0) { s_lo[warp] = lo; s_hi[warp] = hi; } }
-        __syncthreads();
-        if (warp == 0) {
-            // the 8 warp subtrees (slots 8w .. 8w+7): three more levels
-            const int w = lane & 7;
-            double vv = s_val[w];
-            unsigned wp = 0;
-#pragma unroll
-            for (int k = 0; k < BS_THREADS / 32; ++k) wp |= (s_flag[k] & 1u) << k;
-            vv = upsweep_level(vv, w, 1, 1, wp);
-            vv = upsweep_level(vv, w, 2, 1, wp);
-            vv = upsweep_level(vv, w, 4, 1, wp);
-            if (lane == 0) {
-                top_val[(int64_t)f * ntop + node] = present ? vv : 0.0;
-                top_flag[(int64_t)f * ntop + node] = present ? 1 : 0;
-                if (MODE == 0) {
-                    double l2 = s_lo[0], h2 = s_hi[0];
-                    for (int k = 1; k < BS_THREADS / 32; ++k) { l2 = fmin(l2, s_lo[k]); h2 = fmax(h2, s_hi[k]); }
-                    top_min[(int64_t)f * ntop + node] = l2;
-                    top_max[(int64_t)f * ntop + node] = h2;
-                }
-            }
+    }
+    if (MODE == 0) {
+        __shared__ double s_lo[BS_THREADS / 32], s_hi[BS_THREADS / 32];
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
         }
+        if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
         __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < BS_THREADS / 32; ++k) { lo = fmin(lo, s_lo[k]); hi = fmax(hi, s_hi[k]); }
+            cta_min[(int64_t)f * gridDim.x + blockIdx.x] = lo;
+            cta_max[(int64_t)f * gridDim.x + blockIdx.x] = hi;
+        }
     }
 }
 
@@ -272,7 +288,7 @@ block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LT, int
 template <int MODE>
 __global__ void __launch_bounds__(1024)
 block_top_kernel(int LT, double* __restrict__ top_val, const unsigned char* __restrict__ top_flag,
-                 const double* __restrict__ top_min, const double* __restrict__ top_max,
+                 const double* __restrict__ top_min, const double* __restrict__ top_max, int nmm,
                  double* __restrict__ stats)
 {
     const int f = blockIdx.x;
@@ -289,9 +305,9 @@ block_top_kernel(int LT, double* __restrict__ top_val, const unsigned char* __re
     if (MODE == 0) {
         __shared__ double s_lo[32], s_hi[32];
         double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
-        for (int64_t t = threadIdx.x; t < ntop; t += blockDim.x) {
-            lo = fmin(lo, top_min[(int64_t)f * ntop + t]);
-            hi = fmax(hi, top_max[(int64_t)f * ntop + t]);
+        for (int t = threadIdx.x; t < nmm; t += blockDim.x) {
+            lo = fmin(lo, top_min[(int64_t)f * nmm + t]);
+            hi = fmax(hi, top_max[(int64_t)f * nmm + t]);
         }
         for (int o = 16; o > 0; o >>= 1) {
             lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
@@ -301,6 +317,9 @@ block_top_kernel(int LT, double* __restrict__ top_val, const unsigned char* __re
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+            const double inf = __longlong_as_double(0x7FF0000000000000LL);
+            // a NaN element makes the sum NaN (inf - inf does too, but then min/max are -inf/+inf)
+            if (val[0] != val[0] && !(lo == -inf && hi == inf)) lo = hi = val[0];
             stats[f * 4 + 0] = val[0];
             stats[f * 4 + 1] = lo;
             stats[f * 4 + 2] = hi;
@@ -411,9 +430,9 @@ extern "C" int64_t omb_block_stats_ws_bytes(int64_t F, int64_t block_elems)
 {
     if (F <= 0 || block_elems <= 0) return 0;
     BlockPlan p = make_plan(block_elems);
-    int64_t ntop = (int64_t)1 << p.LT;
-    // val + min + max (doubles) + flags, per feature
-    return F * ntop * (3 * (int64_t)sizeof(double)) + round_up(F * ntop, 256) + 256;
+    int64_t ntop = (int64_t)1 << p.LW;
+    // level-LW values + flags, per-CTA min/max partials, per feature
+    return F * ntop * (int64_t)sizeof(double) + round_up(F * ntop, 256) + 2 * F * BS_GX_MAX * (int64_t)sizeof(double) + 256;
 }
 
 extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems, int mode,
@@ -423,28 +442,32 @@ extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems
     OMB_CHECK_ARG(F > 0 && block_elems > 0, "non-positive size");
     OMB_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
     BlockPlan p = make_plan(block_elems);
-    OMB_CHECK_ARG(p.LT <= 30, "block too large");
-    const int64_t ntop = (int64_t)1 << p.LT;
+    OMB_CHECK_ARG(p.LW <= 30, "block too large");
+    const int64_t ntop = (int64_t)1 << p.LW;
     double* top_val = (double*)d_ws;
     double* top_min = top_val + F * ntop;
-    double* top_max = top_min + F * ntop;
-    unsigned char* top_flag = (unsigned char*)(top_max + F * ntop);
-    int64_t gx = ntop;                       // one ~30-60 KB node per CTA
-    if (gx > 65535 * 16) gx = 65535 * 16;
+    double* top_max = top_min + F * BS_GX_MAX;
+    unsigned char* top_flag = (unsigned char*)(top_max + F * BS_GX_MAX);
+    // persistent warps: ~BS_CTAS_PER_SM CTAs per SM over all features, each warp strides over nodes
+    int64_t gx = ceil_div((int64_t)sm_count() * BS_CTAS_PER_SM, F);
+    const int64_t need = ceil_div(ntop, BS_THREADS / 32);
+    if (gx > need) gx = need;
+    if (gx > BS_GX_MAX) gx = BS_GX_MAX;
+    if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)F);
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0)
-        block_tree_kernel<0><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LT, p.LC, d_out, (double)mean_count, top_val,
+        block_tree_kernel<0><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LW, p.LQ, d_out, (double)mean_count, top_val,
                                                            top_flag, top_min, top_max);
     else
-        block_tree_kernel<1><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LT, p.LC, d_out, (double)mean_count, top_val,
+        block_tree_kernel<1><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LW, p.LQ, d_out, (double)mean_count, top_val,
                                                            top_flag, top_min, top_max);
     int rc = check_launch("block_tree_kernel");
     if (rc) return rc;
     if (mode == 0)
-        block_top_kernel<0><<<(unsigned)F, 1024, 0, st>>>(p.LT, top_val, top_flag, top_min, top_max, d_out);
+        block_top_kernel<0><<<(unsigned)F, 1024, 0, st>>>(p.LW, top_val, top_flag, top_min, top_max, (int)gx, d_out);
     else
-        block_top_kernel<1><<<(unsigned)F, 1024, 0, st>>>(p.LT, top_val, top_flag, top_min, top_max, d_out);
+        block_top_kernel<1><<<(unsigned)F, 1024, 0, st>>>(p.LW, top_val, top_flag, top_min, top_max, (int)gx, d_out);
     return check_launch("block_top_kernel");
 }
 

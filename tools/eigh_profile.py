@@ -4,7 +4,7 @@ import torch
 from openmeasure_b200 import synth, engine as E, _lib
 F, n_c, m, r = 9, 183620, 41, 40
 Xd = synth.snapshots(F, n_c, m, r)
-eng = E.Engine(Xd, F, group=False); eng.stats("std", 1); G = eng.gram()
+eng = E.Engine(Xd, F, group=False); eng.stats("std", 1, defer_row_means=True); G = eng.gram()
 w = torch.empty(m, dtype=torch.float64, device="cuda"); V = torch.empty(m, m, dtype=torch.float64, device="cuda")
 info = torch.zeros(1, dtype=torch.int32, device="cuda")
 p = lambda t: C.c_void_p(t.data_ptr())

@@ -7,7 +7,7 @@ F, n_c, m, r = 9, 183620, 41, 40
 Xd = synth.snapshots(F, n_c, m, r)
 eng = E.Engine(Xd, F, group=False)
 for _ in range(2):
-    eng.stats("std", 1)
+    eng.stats("std", 1, defer_row_means=True)
     G = eng.gram()
     S, V = eng.eig_pod(G)
     eng.backproject((V[:, :r] / S[:r]).contiguous())

@@ -24,7 +24,7 @@ def seg(name, fn, sync=True):
 for it in range(4):
     print("iter", it)
     eng = seg("Engine()", lambda: E.Engine(Xd, F, group=False))
-    seg("stats", lambda: eng.stats("std", 1))
+    seg("stats", lambda: eng.stats("std", 1, defer_row_means=True))
     G = seg("gram", lambda: eng.gram())
     S, V = seg("eigh", lambda: eng.eig_pod(G))
     W = seg("W", lambda: (V[:, :r] / S[:r]).contiguous())

@@ -11,7 +11,7 @@ r = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 blocks = [int(b) for b in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 4, 8, 16]
 Xd = synth.snapshots(F, n_c, m, r)
 eng = E.Engine(Xd, F, group=False)
-eng.stats("std", 1)
+eng.stats("std", 1, defer_row_means=True)
 S, V = eng.eig_pod(eng.gram())
 eng.backproject((V[:, :r] / S[:r]).contiguous())
 torch.cuda.synchronize()
