@@ -273,6 +273,197 @@ static int launch_bp_small(const double* X, int64_t n, int64_t n_c, int m, const
     return check_launch("backproject_small_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Many-snapshot / many-mode variant (m or r > 64; m, r even): persistent, TMA-pipelined.
+// One CTA per SM walks the 128-row basis tiles.  32-snapshot K-chunks of the tile's rows of X (one
+// 256-byte bulk copy per row, padded pitch 36 doubles -> conflict-free fragment loads) and of W
+// flow through a 3-stage ring; every warp issues its own share of a chunk's copies two chunks
+// ahead (also across tile boundaries, so the epilogue of a tile overlaps the loads of the next).
+// 8 warps = 4 row groups x 2 column halves, 32 x 8*QH outputs each (up to 128 accumulator
+// registers per lane -- hence 256 threads, not a ninth producer warp: 288 threads cap ptxas at
+// 168 registers).  The epilogue needs no staging: a DMMA accumulator fragment is eight
+// consecutive candidates of one mode, i.e. one 64-byte run of the tiled mode-major layout.
+// ---------------------------------------------------------------------------------------------
+constexpr int BB_K = 32;                    // snapshots per stage
+constexpr int BB_LDA = BB_K + 4;            // == 4 (mod 16)
+constexpr int BB_STAGES = 3;
+constexpr int BB_WARPS = 8;
+constexpr int BB_THREADS = BB_WARPS * 32;
+
+template <int QH>
+struct BbCfg {
+    static constexpr int QC = 16 * QH;                   // modes per launch
+    static constexpr int LDW = QC + 4;                   // == 4 (mod 16)
+    static constexpr int STAGE = OMB_TB * BB_LDA + BB_K * LDW;
+    static constexpr size_t BYTES = sizeof(double) * ((size_t)BB_STAGES * STAGE + 2 * OMB_TB);
+};
+
+template <int QH>
+__global__ void __launch_bounds__(BB_THREADS)
+backproject_big_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, const double* __restrict__ cnt,
+                       const double* __restrict__ scl, const double* __restrict__ W, int r, int q0, int first, int last,
+                       double* __restrict__ Ut, double* __restrict__ vn)
+{
+    using Cfg = BbCfg<QH>;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[BB_STAGES], empty_bar[BB_STAGES];
+    double* s_n = smem + (size_t)BB_STAGES * Cfg::STAGE;         // [2][128] row sums of squares per column half
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = basis_tiles(n);
+    const int nch = (m + BB_K - 1) / BB_K;
+    const int qv = (r - q0) < Cfg::QC ? (r - q0) : Cfg::QC;      // valid modes of this launch (even)
+
+    for (int e = threadIdx.x; e < BB_STAGES * Cfg::STAGE; e += BB_THREADS) smem[e] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BB_STAGES; ++s) { mbar_init(&full_bar[s], BB_WARPS); mbar_init(&empty_bar[s], BB_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- issue side: this warp's share (16 rows of X, 4 rows of W) of chunk `gi`
+    int64_t it_tile = blockIdx.x, gi = 0;
+    int it_c = 0;
+    auto issue = [&]() {
+        if (it_tile >= ntiles) return;
+        const int s = (int)(gi % BB_STAGES);
+        if (gi >= BB_STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((gi / BB_STAGES) - 1) & 1));
+        const int64_t row0 = it_tile * OMB_TB;
+        const int rows = (int)((n - row0) < OMB_TB ? (n - row0) : OMB_TB);
+        const int k0 = it_c * BB_K;
+        const int kv = (m - k0) < BB_K ? (m - k0) : BB_K;
+        int nx = rows - 16 * warp; nx = nx < 0 ? 0 : (nx > 16 ? 16 : nx);
+        int nw = kv - 4 * warp; nw = nw < 0 ? 0 : (nw > 4 ? 4 : nw);
+        double* sA = smem + (size_t)s * Cfg::STAGE;
+        double* sW = sA + OMB_TB * BB_LDA;
+        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(((int64_t)nx * kv + (int64_t)nw * qv) * sizeof(double)));
+        __syncwarp();
+        if (lane < nx) {
+            const int rr = 16 * warp + lane;
+            tma_load_bulk(sA + rr * BB_LDA, X + (row0 + rr) * m + k0, (uint32_t)(kv * sizeof(double)), &full_bar[s]);
+        } else if (lane >= 16 && lane - 16 < nw) {
+            const int kk = 4 * warp + lane - 16;
+            tma_load_bulk(sW + kk * Cfg::LDW, W + (int64_t)(k0 + kk) * r + q0, (uint32_t)(qv * sizeof(double)), &full_bar[s]);
+        }
+        ++gi;
+        if (++it_c == nch) { it_c = 0; it_tile += gridDim.x; }
+    };
+#pragma unroll 1
+    for (int u = 0; u < BB_STAGES - 1; ++u) issue();
+
+    // ---- compute side: warp (wr, wc) owns rows [32 wr, +32) x modes [8 QH wc, +8 QH)
+    const int fr = lane & 3, fc = lane >> 2;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int ib = wr * 32, jb = wc * 8 * QH;
+    int64_t g = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * OMB_TB;
+        double cv[4], sv[4];
+        bool rok[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int64_t row = row0 + ib + 8 * p + fc;
+            rok[p] = row < n;
+            cv[p] = (rok[p] && cnt) ? cnt[row] : 0.0;
+            sv[p] = (rok[p] && scl) ? scl[row / n_c] : 1.0;
+        }
+        double acc[4][QH][2];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < QH; ++q) acc[p][q][0] = acc[p][q][1] = 0.0;
+
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, ++g) {
+            issue();                                           // chunk g + 2 into the stage chunk g - 1 used
+            const int s = (int)(g % BB_STAGES);
+            mbar_wait(&full_bar[s], (uint32_t)((g / BB_STAGES) & 1));
+            const double* sA = smem + (size_t)s * Cfg::STAGE;
+            const double* sW = sA + OMB_TB * BB_LDA;
+            const int kv = (m - c * BB_K) < BB_K ? (m - c * BB_K) : BB_K;
+#pragma unroll
+            for (int k4 = 0; k4 < BB_K / 4; ++k4) {
+                const int kk = k4 * 4 + fr;
+                const bool kok = kk < kv;                      // stale snapshots of a ragged last chunk
+                double a[4], b[QH];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = sA[(ib + 8 * p + fc) * BB_LDA + kk];
+#pragma unroll
+                for (int q = 0; q < QH; ++q) b[q] = sW[kk * Cfg::LDW + jb + 8 * q + fc];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = kok ? a[p] - cv[p] : 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < QH; ++q) dmma884(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        }
+
+        // epilogue: U = acc / scl straight to the tile (64-byte runs), row sums of squares for the norms
+        double* tbase = Ut + tile * ((int64_t)r * OMB_TB);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int i = ib + 8 * p + fc;
+            double ss = 0.0;
+#pragma unroll
+            for (int q = 0; q < QH; ++q) {
+                const int col = jb + 8 * q + 2 * fr;           // mode index inside this launch
+                const double u0 = acc[p][q][0] / sv[p], u1 = acc[p][q][1] / sv[p];
+                if (col < qv) { if (rok[p]) stg_stream(tbase + (int64_t)(q0 + col) * OMB_TB + i, u0); ss = fma(u0, u0, ss); }
+                if (col + 1 < qv) { if (rok[p]) stg_stream(tbase + (int64_t)(q0 + col + 1) * OMB_TB + i, u1); ss = fma(u1, u1, ss); }
+            }
+            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 1);
+            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 2);
+            if (vn && fr == 0) s_n[wc * OMB_TB + i] = ss;
+        }
+        if (vn) {
+            __syncthreads();
+            if (threadIdx.x < OMB_TB && row0 + threadIdx.x < n) {
+                double t = s_n[threadIdx.x] + s_n[OMB_TB + threadIdx.x];
+                double* dst = vn + row0 + threadIdx.x;
+                if (!first) t += *dst;
+                *dst = last ? sqrt(t) : t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int QH>
+static int launch_bp_big(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl,
+                         const double* W, int r, int q0, double* Ut, double* vn, cudaStream_t st)
+{
+    using Cfg = BbCfg<QH>;
+    OMB_CUDA(cudaFuncSetAttribute(backproject_big_kernel<QH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::BYTES));
+    int64_t grid = basis_tiles(n);
+    if (grid > sm_count()) grid = sm_count();
+    const int first = q0 == 0, last = q0 + Cfg::QC >= r;
+    backproject_big_kernel<QH><<<(unsigned)grid, BB_THREADS, Cfg::BYTES, st>>>(X, n, n_c, m, cnt, scl, W, r, q0, first, last, Ut, vn);
+    return check_launch("backproject_big_kernel");
+}
+
+static int bp_big(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl, const double* W,
+                  int r, double* Ut, double* vn, cudaStream_t st)
+{
+    // launches of up to 128 modes; the last one takes the narrowest instantiation that fits
+    for (int q0 = 0; q0 < r; q0 += 128) {
+        const int rem = r - q0;
+        const int qh = rem >= 128 ? 8 : (rem + 15) / 16;
+        int rc;
+        switch (qh) {
+#define OMB_BB(QHV) case QHV: rc = launch_bp_big<QHV>(X, n, n_c, m, cnt, scl, W, r, q0, Ut, vn, st); break;
+            OMB_BB(1) OMB_BB(2) OMB_BB(3) OMB_BB(4) OMB_BB(5) OMB_BB(6) OMB_BB(7) OMB_BB(8)
+#undef OMB_BB
+            default: rc = -1; break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 }  // namespace omb
 
 using namespace omb;
@@ -295,6 +486,8 @@ extern "C" int omb_backproject(const double* d_X, int64_t F, int64_t n_c, int64_
             default: break;
         }
     }
+    if ((m & 1) == 0 && (r & 1) == 0 && ((reinterpret_cast<uintptr_t>(d_X) | reinterpret_cast<uintptr_t>(d_W)) & 15) == 0)
+        return bp_big(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
     if (r <= 64) return launch_bp<8>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
     return launch_bp<16>(d_X, n, n_c, (int)m, d_cnt, d_scl, d_W, (int)r, d_Ut, d_vn, st);
 }

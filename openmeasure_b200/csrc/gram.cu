@@ -128,6 +128,150 @@ gram_tile_kernel(const double* __restrict__ X, int64_t n_c, int m, const double*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Many-snapshot variant (m > 64, even): 128 x 128 output tiles, warp-specialised.  A producer warp
+// streams 16-row K-chunks of the two column panels of X through a 5-stage shared-memory ring with
+// one bulk (TMA) copy per row and panel (rows land at a padded pitch of 132 doubles, so the
+// fragment loads are bank-conflict free); 8 consumer warps own 32 x 64 outputs each (64 DMMA
+// accumulators per lane).  A 64 x 64 tile needs 4.6 TB/s of operand traffic to keep the FP64
+// tensor pipe busy, a 128 x 128 tile half of that -- it comes from the L2, where the tile pairs of
+// a row split meet.  Centring is a DADD on the fragment (the raw tile is what TMA delivers).
+// ---------------------------------------------------------------------------------------------
+constexpr int GB_T = 128;                         // output tile edge
+constexpr int GB_K = 16;                          // rows per stage
+constexpr int GB_LD = GB_T + 4;                   // == 4 (mod 16)
+constexpr int GB_STAGES = 5;
+constexpr int GB_WARPS = 8;
+constexpr int GB_THREADS = (GB_WARPS + 1) * 32;
+constexpr int GB_STAGE_DOUBLES = 2 * GB_K * GB_LD + GB_K;      // panel A, panel B, centring values
+
+static size_t gram_big_smem() { return sizeof(double) * GB_STAGES * GB_STAGE_DOUBLES; }
+
+__global__ void __launch_bounds__(GB_THREADS, 1)
+gram_big_kernel(const double* __restrict__ X, int64_t n_c, int m, const double* __restrict__ cnt, int T,
+                int64_t rows_per_split, int splits, double* __restrict__ part)
+{
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[GB_STAGES], empty_bar[GB_STAGES];
+
+    int ti, tj;
+    tile_pair(blockIdx.x, T, ti, tj);
+    const int split = blockIdx.y, f = blockIdx.z;
+    const bool diag = (ti == tj);
+    const int64_t row_lo = (int64_t)split * rows_per_split;
+    int64_t row_hi = row_lo + rows_per_split;
+    if (row_hi > n_c) row_hi = n_c;
+    const double* Xf = X + (int64_t)f * n_c * m;
+    const double* cf = cnt ? cnt + (int64_t)f * n_c : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunks = (int)ceil_div(row_hi - row_lo, GB_K);
+    const int ca0 = ti * GB_T, cb0 = tj * GB_T;
+    const int wa = (m - ca0) < GB_T ? (m - ca0) : GB_T;       // valid columns of the two panels (even)
+    const int wb = (m - cb0) < GB_T ? (m - cb0) : GB_T;
+
+    // columns beyond m are never written by the copies: zero the whole ring once
+    for (int e = threadIdx.x; e < GB_STAGES * GB_STAGE_DOUBLES; e += GB_THREADS) smem[e] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], GB_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == GB_WARPS) {
+        // ---------------- producer warp: lane l < 16 copies row l of panel A, lane 16 + l row l of panel B
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % GB_STAGES;
+            if (c >= GB_STAGES) mbar_wait(&empty_bar[s], ((c / GB_STAGES) - 1) & 1);
+            const int64_t k0 = row_lo + (int64_t)c * GB_K;
+            const int rows = (int)((row_hi - k0) < GB_K ? (row_hi - k0) : GB_K);
+            double* stage = smem + (size_t)s * GB_STAGE_DOUBLES;
+            double* sCn = stage + 2 * GB_K * GB_LD;
+            if (lane < GB_K) sCn[lane] = (cf && lane < rows) ? cf[k0 + lane] : 0.0;
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(rows * (wa + (diag ? 0 : wb)) * sizeof(double)));
+            __syncwarp();
+            const int rr = lane & (GB_K - 1);
+            if (rr < rows) {
+                if (lane < GB_K) tma_load_bulk(stage + rr * GB_LD, Xf + (k0 + rr) * m + ca0, (uint32_t)(wa * sizeof(double)), &full_bar[s]);
+                else if (!diag) tma_load_bulk(stage + (GB_K + rr) * GB_LD, Xf + (k0 + rr) * m + cb0, (uint32_t)(wb * sizeof(double)), &full_bar[s]);
+            }
+        }
+    } else {
+        // ---------------- consumer warps: warp (wr, wc) owns G rows [32 wr, +32) x columns [64 wc, +64)
+        const int fr = lane & 3, fc = lane >> 2;
+        const int ib = (warp >> 1) * 32, jb = (warp & 1) * 64;
+        double c[4][8][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % GB_STAGES;
+            mbar_wait(&full_bar[s], (ch / GB_STAGES) & 1);
+            const double* sA = smem + (size_t)s * GB_STAGE_DOUBLES;
+            const double* sB = diag ? sA : sA + GB_K * GB_LD;
+            const double* sCn = sA + 2 * GB_K * GB_LD;
+            const int rows = (int)((row_hi - (row_lo + (int64_t)ch * GB_K)) < GB_K ? (row_hi - (row_lo + (int64_t)ch * GB_K)) : GB_K);
+#pragma unroll
+            for (int k4 = 0; k4 < GB_K / 4; ++k4) {
+                const int kr = k4 * 4 + fr;
+                const bool kok = kr < rows;                // stale rows of a ragged last chunk
+                const double cv = sCn[kr];
+                double a[4], b[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = sA[kr * GB_LD + ib + q * 8 + fc];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = sB[kr * GB_LD + jb + q * 8 + fc];
+                const bool aok[4] = {ib + fc < wa, ib + 8 + fc < wa, ib + 16 + fc < wa, ib + 24 + fc < wa};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = (kok && aok[q]) ? a[q] - cv : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = (kok && (jb + q * 8 + fc) < wb) ? b[q] - cv : 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dmma884(c[p][q][0], c[p][q][1], a[p], b[q]);
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        }
+
+        // partial tile: part[f][split][tile][GB_T][GB_T]
+        double* out = part + (((int64_t)f * splits + split) * gridDim.x + blockIdx.x) * (GB_T * GB_T);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = ib + p * 8 + fc;
+                const int j = jb + q * 8 + 2 * fr;
+                *reinterpret_cast<double2*>(out + i * GB_T + j) = make_double2(c[p][q][0], c[p][q][1]);
+            }
+    }
+}
+
+static GramPlan gram_big_plan(int64_t F, int64_t n_c, int64_t m)
+{
+    GramPlan p;
+    p.T = (int)ceil_div(m, GB_T);
+    p.ntiles = p.T * (p.T + 1) / 2;
+    // one CTA per SM (shared memory): aim at one full wave, or whole waves when the tiles alone exceed it
+    int64_t splits = (int64_t)sm_count() / ((int64_t)F * p.ntiles);
+    if (splits < 1) splits = 1;
+    int64_t max_splits = ceil_div(n_c, 8 * GB_K);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.rows_per_split = round_up(ceil_div(n_c, splits), GB_K);
+    p.splits = (int)ceil_div(n_c, p.rows_per_split);
+    return p;
+}
+
+static bool gram_big_ok(const double* X, int64_t m)
+{
+    return m > 64 && (m & 1) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Few-snapshot variant (m <= 64): the whole m x m Gram fits one warp's accumulators, so every
 // warp sweeps its own rows and keeps the NB(NB+1)/2 upper-triangular 8 x 8 blocks (NB = ceil(m/8))
 // in registers.  A fragment X[k0 + lane%4][8b + lane/4] serves as both operands of the symmetric
@@ -323,7 +467,7 @@ static GramPlan gram_small_plan(int64_t F, int64_t n_c)
 
 // Gf[f][i][j] = sum over splits (fixed order) of the tile holding (min-tile, max-tile); mirrored.
 __global__ void __launch_bounds__(256)
-gram_reduce_kernel(const double* __restrict__ part, int m, int T, int ntiles, int splits,
+gram_reduce_kernel(const double* __restrict__ part, int m, int T, int ntiles, int splits, int gt,
                    double* __restrict__ Gf)
 {
     const int f = blockIdx.y;
@@ -332,11 +476,11 @@ gram_reduce_kernel(const double* __restrict__ part, int m, int T, int ntiles, in
          e += (int64_t)gridDim.x * blockDim.x) {
         int i = (int)(e / m), j = (int)(e - (int64_t)i * m);
         if (i > j) { int t = i; i = j; j = t; }          // read the upper triangle, mirror
-        const int ti = i / GT, tj = j / GT;
+        const int ti = i / gt, tj = j / gt;
         const int tile = ti * T - ti * (ti - 1) / 2 + (tj - ti);
-        const double* p = part + ((int64_t)f * splits * ntiles + tile) * (GT * GT) + (i % GT) * GT + (j % GT);
+        const double* p = part + ((int64_t)f * splits * ntiles + tile) * (gt * gt) + (i % gt) * gt + (j % gt);
         double s = 0.0;
-        for (int sp = 0; sp < splits; ++sp) s += p[(int64_t)sp * ntiles * (GT * GT)];
+        for (int sp = 0; sp < splits; ++sp) s += p[(int64_t)sp * ntiles * (gt * gt)];
         Gf[(int64_t)f * mm + e] = s;
     }
 }
@@ -364,8 +508,15 @@ using namespace omb;
 extern "C" int64_t omb_gram_ws_bytes(int64_t F, int64_t n_c, int64_t m)
 {
     if (F <= 0 || n_c <= 0 || m <= 0) return 0;
-    GramPlan p = (m <= 64) ? gram_small_plan(F, n_c) : gram_plan(F, n_c, m);
-    return (int64_t)sizeof(double) * F * p.splits * p.ntiles * GT * GT;
+    if (m <= 64) {
+        GramPlan p = gram_small_plan(F, n_c);
+        return (int64_t)sizeof(double) * F * p.splits * p.ntiles * GT * GT;
+    }
+    // the larger of the two many-snapshot layouts (which one runs depends on the alignment of X)
+    GramPlan p = gram_plan(F, n_c, m), q = gram_big_plan(F, n_c, m);
+    const int64_t a = (int64_t)sizeof(double) * F * p.splits * p.ntiles * GT * GT;
+    const int64_t b = (int64_t)sizeof(double) * F * q.splits * q.ntiles * GB_T * GB_T;
+    return a > b ? a : b;
 }
 
 namespace omb {
@@ -402,6 +553,7 @@ int omb::gram_impl(const double* d_X, int64_t F, int64_t n_c, int64_t m, const d
     cudaStream_t st = (cudaStream_t)stream;
     GramPlan p;
     int rc;
+    int gt = GT;
     if (m <= 64) {
         p = gram_small_plan(F, n_c);
         dim3 grid((unsigned)p.splits, (unsigned)F);
@@ -410,6 +562,14 @@ int omb::gram_impl(const double* d_X, int64_t F, int64_t n_c, int64_t m, const d
         OMB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<grid, GS_THREADS, smem, st>>>(d_X, n_c, (int)m, d_cnt, d_cnt_out, p.rows_per_split, p.splits, (double*)d_ws);
         rc = check_launch("gram_small_kernel");
+    } else if (gram_big_ok(d_X, m)) {
+        p = gram_big_plan(F, n_c, m);
+        gt = GB_T;
+        dim3 grid((unsigned)p.ntiles, (unsigned)p.splits, (unsigned)F);
+        OMB_CUDA(cudaFuncSetAttribute(gram_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_big_smem()));
+        gram_big_kernel<<<grid, GB_THREADS, gram_big_smem(), st>>>(d_X, n_c, (int)m, d_cnt, p.T, p.rows_per_split, p.splits,
+                                                                  (double*)d_ws);
+        rc = check_launch("gram_big_kernel");
     } else {
         p = gram_plan(F, n_c, m);
         dim3 grid((unsigned)p.ntiles, (unsigned)p.splits, (unsigned)F);
@@ -421,7 +581,7 @@ int omb::gram_impl(const double* d_X, int64_t F, int64_t n_c, int64_t m, const d
     int64_t gx = ceil_div(m * m, 256);
     if (gx > 2048) gx = 2048;
     dim3 rgrid((unsigned)gx, (unsigned)F);
-    gram_reduce_kernel<<<rgrid, 256, 0, st>>>((const double*)d_ws, (int)m, p.T, p.ntiles, p.splits, d_Gf);
+    gram_reduce_kernel<<<rgrid, 256, 0, st>>>((const double*)d_ws, (int)m, p.T, p.ntiles, p.splits, gt, d_Gf);
     return check_launch("gram_reduce_kernel");
 }
 

@@ -451,3 +451,33 @@ def test_eigh_jacobi_matches_lapack(torch_cuda, m, kind):
     np.testing.assert_allclose(V.T @ V, np.eye(m), atol=1e-13)
     np.testing.assert_allclose(G @ V, V * w, atol=1e-13 * scale * max(m, 4))
     assert np.all(np.diff(w) <= 0) and 0 < int(info.item()) + 1 <= 30
+
+
+# ---------------------------------------------------------------------------------------------
+# K3/K5: Gram and back-projection kernels against numpy over the kernel-selection boundaries
+# (m <= 64 register-resident variant with fused row means; even m > 64 TMA-pipelined 128 x 128
+# tiles; odd m > 64 staged 64 x 64 tiles) and ragged row counts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,n_c,m,r", [(2, 37, 8, 3), (3, 1000, 41, 14), (2, 515, 64, 20), (2, 700, 66, 30),
+                                       (2, 333, 128, 64), (1, 2049, 130, 100), (3, 900, 256, 100),
+                                       (2, 450, 300, 128), (2, 611, 129, 40), (1, 300, 640, 200)])
+def test_gram_and_backprojection_match_numpy(torch_cuda, F, n_c, m, r):
+    torch = torch_cuda
+    from openmeasure_b200 import engine as E
+    rng = np.random.default_rng(F * 1000 + m)
+    X = rng.random((F * n_c, m)) * 10.0 ** rng.integers(-1, 2, (F * n_c, 1)) + 3.0
+    eng = E.Engine(torch.from_numpy(X).cuda(), F, group=False)
+    eng.stats("std", 1, defer_row_means=True)
+    G = eng.gram().cpu().numpy()
+    np.testing.assert_array_equal(eng.cnt.cpu().numpy(), np.mean(X, axis=1))       # fused row means: bit-exact
+    scl = np.repeat([np.std(X[f * n_c:(f + 1) * n_c]) for f in range(F)], n_c)[:, None]
+    X0 = (X - np.mean(X, axis=1)[:, None]) / scl
+    Gref = X0.T @ X0
+    np.testing.assert_allclose(G, Gref, rtol=0, atol=2e-13 * np.abs(Gref).max())
+    np.testing.assert_array_equal(G, G.T)
+    W = rng.standard_normal((m, r))
+    eng.backproject(torch.from_numpy(W).cuda())
+    U = eng.basis_rows().cpu().numpy()
+    Uref = X0 @ W
+    np.testing.assert_allclose(U, Uref, rtol=0, atol=2e-13 * np.abs(Uref).max())
+    np.testing.assert_allclose(eng.vn.cpu().numpy()[:F * n_c], np.linalg.norm(Uref, axis=1), rtol=1e-12)
