@@ -250,7 +250,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-    clocks = Clocks(local_rank) if rank == 0 else None
+    clocks = Clocks(local_rank) if rank == 0 and not os.environ.get("OMB_BENCH_NO_CLOCKS") else None
     if clocks:
         clocks.start()
     L.omb_launch_count_reset()

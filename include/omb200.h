@@ -152,6 +152,23 @@ int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s, const doub
                  const void* d_peers, double* d_mine, int64_t epoch, int64_t* d_piv, double* d_rdiag,
                  double* d_gap, void* stream);
 
+/* ---- GEM: greedy entropy-maximisation placement (SPR.gem, sparse_sensing.py:586-698; reached via
+ *      optimal_placement(calc_type='gem') :745-751).  One streaming pass over the basis per sensor.
+ *      omb_gem_variance: d_var[j] = np.var(Ur[j, :], ddof=1)                              (:621, :639)
+ *      omb_gem_step:     argmax over live candidates of
+ *                        coef^2 var[j] - Sigma_ya B Sigma_ay   (k chosen rows Z (k x r, centred and
+ *                        scaled by coef), B = inverse covariance of the chosen rows, k x k; :670-681);
+ *                        writes the winner's index (-1: none alive), value and UNSCALED basis row.
+ *      omb_gem_exclude:  alive[j] &= ||xyz[j % n_c] - xyz[sensor % n_c]|| >= d_min         (:646-649) */
+int64_t omb_gem_ws_bytes(void);
+int omb_gem_max_sensors(void);
+int omb_gem_variance(const double* d_Ut, int64_t n, int64_t r, double* d_var, void* stream);
+int omb_gem_step(const double* d_Ut, int64_t n, int64_t r, double coef, int64_t k, const double* d_Z,
+                 const double* d_B, const double* d_var, const unsigned char* d_alive, void* d_ws,
+                 int64_t* d_idx, double* d_val, double* d_row, void* stream);
+int omb_gem_exclude(const double* d_xyz, int64_t n_c, int64_t n, const int64_t* d_sensor, double d_min,
+                    unsigned char* d_alive, void* stream);
+
 /* ---- K8/K9: train = row gather (replaces the dense C.dot(Ur), C.dot(X_cnt);
  *      sparse_sensing.py:797, :573).  d_Theta is s x r row-major, d_cnt_s may be NULL. -------- */
 int omb_gather_rows(const double* d_Ut, int64_t r, const int64_t* d_piv, int64_t s,

@@ -39,6 +39,11 @@ SIGNATURES = {
     "omb_qrcp_p2p_buffer_doubles": (_i64, [_int]),
     "omb_qrcp_p2p": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _i64, _i64, _int, _int, _vp, _vp,
                              _i64, _vp, _vp, _vp, _vp]),
+    "omb_gem_ws_bytes": (_i64, []),
+    "omb_gem_max_sensors": (_int, []),
+    "omb_gem_variance": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "omb_gem_step": (_int, [_vp, _i64, _i64, C.c_double, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "omb_gem_exclude": (_int, [_vp, _i64, _i64, _vp, C.c_double, _vp, _vp]),
     "omb_gather_rows": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "omb_modes_to_rows": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "omb_rows_to_modes": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -75,6 +75,17 @@ def p2p_state(comm, device, ndoubles):
     return st if st["hdl"] is not None else None
 
 
+def p2p_why_not(comm):
+    """Why the peer-memory exchange is not in use for `comm` (diagnostics for bench.py / logs)."""
+    import os
+    if not isinstance(comm, TorchDistComm):
+        return "communicator is not torch.distributed"
+    if os.environ.get("OMB_QR_EXCHANGE", "p2p") != "p2p":
+        return "OMB_QR_EXCHANGE=" + os.environ["OMB_QR_EXCHANGE"]
+    key = (id(comm.group) if comm.group is not None else 0, comm.world)
+    return str(_P2P_CACHE.get(key, {}).get("error", "unknown"))
+
+
 class _ThreadShared:
     def __init__(self, world):
         self.slots = [None] * world

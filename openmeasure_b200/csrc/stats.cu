@@ -284,6 +284,42 @@ block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LW, int
     }
 }
 
+// Row means for rows of up to 1024 snapshots: the block-tree machinery applied per row.  A row's
+// numpy tree has S = 2^D <= 8 leaf slots; a warp evaluates 8 / S rows at once, one quad per slot
+// (128-bit loads, up to 256 bytes in flight per lane), and combines a row's slots by shuffles.
+__global__ void __launch_bounds__(BS_THREADS, BS_CTAS_PER_SM)
+row_means_quad_kernel(const double* __restrict__ X, int64_t rows, int m, int D, double* __restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane & 3, sl = lane >> 2;
+    const unsigned qmask = 0xFu << (lane & 28);
+    const int S = 1 << D, rows_per_warp = 8 >> D;
+    const bool xal = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    const double dm = (double)m;
+    const int64_t nwarps = (int64_t)gridDim.x * (BS_THREADS / 32);
+    const int64_t ngroups = ceil_div(rows, (int64_t)rows_per_warp);
+    for (int64_t grp = (int64_t)blockIdx.x * (BS_THREADS / 32) + warp; grp < ngroups; grp += nwarps) {
+        const int64_t row = grp * rows_per_warp + (sl >> D);
+        int64_t off = 0, n = m;
+        bool here = row < rows;
+        if (here) here = descend(off, n, (uint32_t)(sl & (S - 1)), D);
+        double v = 0.0, lo = 0.0, hi = 0.0;
+        if (here) {
+            const double* a = X + row * m + off;
+            const bool vec = xal && (((row * m) & 1) == 0);
+            v = leaf_sum_quad<MapId, false>(a, (int)n, q, qmask, vec, MapId(), lo, hi);
+        }
+        const unsigned hb = __ballot_sync(0xFFFFFFFFu, here);
+        unsigned pres = 0;
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) pres |= ((hb >> (4 * sidx)) & 1u) << sidx;
+        if (S > 1) v = upsweep_level(v, sl, 1, 4, pres);
+        if (S > 2) v = upsweep_level(v, sl, 2, 4, pres);
+        if (S > 4) v = upsweep_level(v, sl, 4, 4, pres);
+        if (q == 0 && (sl & (S - 1)) == 0 && row < rows) cnt[row] = v / dm;
+    }
+}
+
 // One CTA per feature: sweep the top LT levels in place, reduce min/max, write stats.
 template <int MODE>
 __global__ void __launch_bounds__(1024)
@@ -418,6 +454,14 @@ extern "C" int omb_row_means(const double* d_X, int64_t rows, int64_t m, double*
 {
     OMB_CHECK_ARG(d_X && d_cnt, "null pointer");
     OMB_CHECK_ARG(rows > 0 && m > 0, "non-positive size");
+    const BlockPlan rp = make_plan(m);
+    if (m >= 32 && rp.D <= 3) {
+        int64_t g = ceil_div(ceil_div(rows, (int64_t)(8 >> rp.D)), BS_THREADS / 32);
+        const int64_t cap2 = (int64_t)sm_count() * BS_CTAS_PER_SM;
+        if (g > cap2) g = cap2;
+        row_means_quad_kernel<<<(unsigned)g, BS_THREADS, 0, (cudaStream_t)stream>>>(d_X, rows, (int)m, rp.D, d_cnt);
+        return check_launch("row_means_quad_kernel");
+    }
     int64_t groups_per_cta = RM_THREADS / 8;
     int64_t grid = ceil_div(rows, groups_per_cta);
     int64_t cap = (int64_t)sm_count() * 32;

@@ -212,6 +212,13 @@ class Engine:
         _lib.call("omb_rows_to_modes", _p(Ur_dev), n, r, _p(Ut), _p(vn), _stream())
         self.Ut, self.vn, self.r = Ut, vn, r
 
+    def tiled_copy(self, Ur_dev):
+        """Tiled mode-major copy of an (n_loc, r) matrix (does not touch the installed basis)."""
+        Ur_dev = Ur_dev.contiguous()
+        Ut = self._new_basis(int(Ur_dev.shape[1]))
+        _lib.call("omb_rows_to_modes", _p(Ur_dev), self.n_loc, int(Ur_dev.shape[1]), _p(Ut), None, _stream())
+        return Ut
+
     def basis_rows(self):
         """(n_loc, r) C-order copy of the basis on device."""
         out = torch.empty(self.n_loc, self.r, dtype=torch.float64, device=self.dev)
@@ -243,6 +250,7 @@ class Engine:
             return piv, rdiag, gap
         L = _lib.load()
         p2p = _comm.p2p_state(self.comm, self.dev, int(L.omb_qrcp_p2p_buffer_doubles(self.world)))
+        self.qr_exchange = "p2p" if p2p is not None else "allgather: " + _comm.p2p_why_not(self.comm)
         if p2p is not None:
             # the kernels exchange the per-step records themselves over NVLink peer memory
             p2p["epoch"] += 1
@@ -262,6 +270,65 @@ class Engine:
             _lib.call("omb_qrcp_mr_step", _p(self.Ut), _p(work), self.n_loc, r, s, _p(ws), block, i, *sh,
                       _p(recs), _p(piv), _p(rdiag), _p(gap), _stream())
         return piv, rdiag, gap
+
+    # ------------------------------------------------------------------------------------ GEM
+    def gem(self, n_sensors, mask_dev=None, xyz_dev=None, d_min=0.0, Ut=None, normal=None, verbose=False):
+        """Greedy entropy-maximisation placement (sparse_sensing.py:586-698): one streaming pass over
+        the basis per sensor; the k x k covariance inverse (with the reference's random jitter, drawn
+        through `normal` exactly where the reference calls np.random.normal) is formed on the host
+        from the chosen rows.  Returns the sensor row indices (numpy int64)."""
+        if self.world > 1:
+            raise NotImplementedError("GEM placement is single-rank in this build")
+        L = _lib.load()
+        if n_sensors > int(L.omb_gem_max_sensors()):
+            raise ValueError("n_sensors exceeds the supported %d" % int(L.omb_gem_max_sensors()))
+        if normal is None:
+            normal = lambda size: np.random.normal(size=size)
+        Ut = self.Ut if Ut is None else Ut
+        r = int(Ut.shape[1])
+        n, st = self.n_loc, _stream()
+        var = torch.empty(n, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_gem_variance", _p(Ut), n, r, _p(var), st)
+        alive = torch.ones(n, dtype=torch.uint8, device=self.dev) if mask_dev is None \
+            else mask_dev.to(torch.uint8).contiguous()
+        sigma_max = float(torch.where(alive.bool(), var, torch.full_like(var, -1.0)).max())
+        coef = 1 / np.sqrt(sigma_max) * 2                  # :622
+        ws = _ws(L.omb_gem_ws_bytes(), self.dev)
+        idx = torch.empty(1, dtype=torch.int64, device=self.dev)
+        val = torch.empty(1, dtype=torch.float64, device=self.dev)
+        row = torch.empty(r, dtype=torch.float64, device=self.dev)
+        sensors, rows, H_tot = [], [], 0.0
+        if verbose:
+            print(f"{'-'*70} \n {'# sensors':^10} {'sigma^2 y':^10} {'sigma^2 y|a':^10} {'Htot':^10} \n ")
+        for s in range(int(n_sensors)):
+            k, Zd, Bd = len(sensors), None, None
+            if k > 0:
+                A = np.asarray(rows) * coef                # Ur_scl[sensor_list_glb, :]
+                Sigma_aa = np.cov(A, ddof=1)               # :660
+                if s == 1:
+                    B = np.atleast_2d(1 / Sigma_aa)        # :663
+                else:
+                    noise = 1e-5 * normal(Sigma_aa.shape[0])           # :667
+                    B = np.linalg.inv(Sigma_aa + np.diag(noise))
+                Zd = torch.from_numpy(np.ascontiguousarray(A - A.mean(axis=1, keepdims=True))).to(self.dev)
+                Bd = torch.from_numpy(np.ascontiguousarray(B)).to(self.dev)
+            _lib.call("omb_gem_step", _p(Ut), n, r, C.c_double(coef), k, _p(Zd), _p(Bd), _p(var), _p(alive), _p(ws),
+                      _p(idx), _p(val), _p(row), st)
+            if d_min > 0.0:                                # :646-649 (d_min == 0 keeps every candidate)
+                _lib.call("omb_gem_exclude", _p(xyz_dev), self.n_c_loc, n, _p(idx), C.c_double(d_min), _p(alive), st)
+            i = int(idx.item())
+            if i < 0:
+                break                                      # every candidate excluded
+            sensors.append(i)
+            rows.append(row.cpu().numpy().copy())
+            if verbose:
+                v = float(val.item())
+                if s == 0:
+                    print(f"{s+1:^10} {v:^10.2e} {'  -':^10} {'  -':^10}")
+                else:
+                    H_tot += 0.5 * np.log(v) + 0.5 * (np.log(2 * np.pi) + 1)
+                    print(f"{s+1:^10} {float(var[i]) * coef**2:^10.2e} {v:^10.2e} {H_tot:^10.2e}")
+        return np.asarray(sensors, dtype=np.int64)
 
     # ------------------------------------------------------------------------------- K8 - K11
     def gather(self, piv_dev):

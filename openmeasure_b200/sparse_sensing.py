@@ -210,12 +210,39 @@ class ROM:
         for k in ("X_cnt", "X_scl", "X0"):
             self._host.pop(k, None)
 
-    def unscale_data(self, x0, sampling=None):
-        """x = X_scl * x0 + X_cnt (sparse_sensing.py:212-240)."""
+    def _sampled(self, sampling):
+        """(S Ur, S X_scl, S X_cnt) on the device for a sampling matrix S (s_out x n): a row gather
+        when S is one-hot (SensorMatrix or dense), a dense product otherwise (:233, :366)."""
         eng = self._engine()
-        if sampling is not None:
-            raise NotImplementedError('sampling matrices are a "next" row (SURVEY.md 8f)')
+        if sampling.shape[1] != self._n_rows():
+            raise ValueError('The number of columns of the sampling matrix does not match the number'
+                             ' of rows of X.')
+        piv = _as_pivots(sampling)
+        if piv is not None and eng.world == 1:
+            pd = torch.from_numpy(piv).to(eng.dev)
+            SU, cnt_s = (eng.gather(pd) if eng.Ut is not None else (None, eng.cnt[pd]))
+            scl_s = eng.scl[pd // eng.n_c_loc]
+            return SU, scl_s, cnt_s
+        if eng.world > 1:
+            raise NotImplementedError('general sampling matrices are single-rank in this build')
+        Sd = self._dense_to_device(sampling, eng)
+        SU = Sd @ eng.basis_rows() if eng.Ut is not None else None
+        scl_rows = torch.repeat_interleave(eng.scl, eng.n_c_loc)
+        return SU, Sd @ scl_rows, Sd @ eng.cnt
+
+    @staticmethod
+    def _dense_to_device(C, eng):
+        if hasattr(C, "toarray") and not isinstance(C, np.ndarray):
+            C = C.toarray()
+        return torch.from_numpy(np.ascontiguousarray(C, dtype=np.float64)).to(eng.dev)
+
+    def unscale_data(self, x0, sampling=None):
+        """x = X_scl * x0 + X_cnt, or (S X_scl) * x0 + S X_cnt (sparse_sensing.py:212-240)."""
+        eng = self._engine()
         xd = torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float64)).to(eng.dev)
+        if sampling is not None:
+            _, scl_s, cnt_s = self._sampled(sampling)
+            return (scl_s * xd + cnt_s).cpu().numpy()
         return eng.unscale(xd).cpu().numpy()
 
     # ------------------------------------------------------------------ POD (a3, a4)
@@ -324,13 +351,14 @@ class ROM:
     # ------------------------------------------------------------------ reconstruct (a11)
     def reconstruct(self, Ar, sampling=None):
         """X_rec (n, N) = unscale(Ur @ Ar.T) (sparse_sensing.py:342-375)."""
-        if sampling is not None:
-            raise NotImplementedError('sampling matrices are a "next" row (SURVEY.md 8f)')
         Ar = np.asarray(Ar, dtype=np.float64)
         if Ar.ndim < 2:
             Ar = Ar[np.newaxis, :]
         eng = self._engine()
         Ad = torch.from_numpy(np.ascontiguousarray(Ar)).to(eng.dev)
+        if sampling is not None:                          # :365-368: (S Ur) Ar^T, sampled unscaling
+            SU, scl_s, cnt_s = self._sampled(sampling)
+            return (scl_s[:, None] * (SU @ Ad.T) + cnt_s[:, None]).cpu().numpy()
         return eng.reconstruct(Ad).cpu().numpy()
 
     # ------------------------------------------------------------------ out of scope
@@ -350,14 +378,40 @@ class SPR(ROM):
     def __init__(self, X, n_features, xyz):
         super().__init__(X, n_features, xyz)
 
+    # ------------------------------------------------------------------ GEM placement (8f row 1)
+    def gem(self, Ur, n_sensors, mask, d_min, verbose):
+        """Greedy entropy-maximisation placement (sparse_sensing.py:586-698): the row indices of the
+        n_sensors sensors.  Ur: (n, r) basis (None: the fitted basis already on the device).  The
+        reference's random covariance jitter (:667) is drawn with the same np.random.normal calls, so
+        seeding numpy's global generator reproduces the reference's selection."""
+        eng = self._engine()
+        Ut = None
+        if Ur is not None and Ur is not self._host.get("Ur"):
+            Urd = torch.from_numpy(np.ascontiguousarray(Ur, dtype=np.float64)).to(eng.dev)
+            if Urd.shape[0] != eng.n_loc:
+                raise ValueError('Ur must have one row per row of X')
+            Ut = eng.tiled_copy(Urd)
+        elif eng.Ut is None:
+            raise ValueError('gem() needs a fitted basis')
+        mask_d = None if mask is None else torch.from_numpy(np.asarray(mask, dtype=bool)).to(eng.dev)
+        xyz_d = None
+        if d_min > 0:
+            if self.xyz is None:
+                raise TypeError('d_min > 0 needs the cell coordinates xyz')
+            xyz_d = torch.from_numpy(np.ascontiguousarray(self.xyz, dtype=np.float64)).to(eng.dev)
+            if xyz_d.shape != (eng.n_c_loc, 3):
+                raise ValueError('xyz must be (n_points, 3)')
+        return eng.gem(n_sensors, mask_d, xyz_d, float(d_min), Ut=Ut, verbose=verbose)
+
     # ------------------------------------------------------------------ placement (a7)
     def optimal_placement(self, calc_type='qr', n_sensors=10, mask=None, d_min=0., verbose=False,
                           block=8):
         """QR-with-column-pivoting sensor placement (sparse_sensing.py:700-756, 'qr' branch).
         `n_sensors`, `d_min`, `verbose` are ignored for 'qr' exactly as in the reference.
         `block` (extension) = pivot steps between trailing-matrix rewrites."""
-        if calc_type == 'gem':
-            raise NotImplementedError('GEM placement is a "next" row (SURVEY.md 8f)')
+        if calc_type == 'gem':                            # :745-751
+            P = self.gem(self.Ur if "Ur" in self._host else None, n_sensors, mask, d_min, verbose)
+            return SensorMatrix(P, self._n_rows())
         if calc_type != 'qr':
             raise NotImplementedError('The sensor selection method has not been implemented yet')
         eng = self._engine()
@@ -407,12 +461,6 @@ class SPR(ROM):
             Sth = torch.linalg.svdvals(Theta_d if Theta_d.shape[0] == Theta_d.shape[1]
                                        else torch.linalg.pinv(Theta_d, rtol=1e-15))
             self.k = float(Sth[0] / Sth[-1])
-
-    @staticmethod
-    def _dense_to_device(C, eng):
-        if hasattr(C, "toarray") and not isinstance(C, np.ndarray):
-            C = C.toarray()
-        return torch.from_numpy(np.ascontiguousarray(C, dtype=np.float64)).to(eng.dev)
 
     # ------------------------------------------------------------------ predict (a9, a10)
     def scale_vector(self, y):
@@ -477,6 +525,3 @@ class SPR(ROM):
             Asig[idx] = torch.bmm(P, y0s.unsqueeze(2)).squeeze(2).abs()
         self.scale_vector(y[-1])                # leaves cnt_vector / scl_vector like the reference
         return Ar.cpu().numpy(), Asig.cpu().numpy()
-
-    def gem(self, *args, **kwargs):
-        raise NotImplementedError('GEM placement is a "next" row (SURVEY.md 8f)')

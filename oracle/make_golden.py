@@ -80,25 +80,49 @@ def _case(sps, name, X, F, n_modes, select_modes="number", scale_type="std", axi
     print(f"{name}: n={n} m={m} r={spr.r} piv[:6]={piv[:6]} -> {os.path.getsize(path)/1e3:.0f} kB")
 
 
+def _gem_case(sps, name, X, F, n_modes, n_sensors, d_min, seed, rng):
+    """optimal_placement(calc_type='gem') of the unmodified reference; its random jitter
+    (sparse_sensing.py:667) is made reproducible by seeding numpy's global generator."""
+    n, m = X.shape
+    n_c = n // F
+    xyz = rng.random((n_c, 3))
+    mask = rng.random(n) > 0.1
+    spr = sps.SPR(X.copy(), F, xyz)
+    spr.fit(select_modes="number", n_modes=n_modes)
+    np.random.seed(seed)
+    C = spr.optimal_placement(calc_type="gem", n_sensors=n_sensors, mask=mask, d_min=d_min)
+    piv = np.argmax(C, axis=1).astype(np.int64)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, X=X, F=np.int64(F), n_modes=np.int64(n_modes), xyz=xyz, mask=mask, Ur=spr.Ur,
+                        n_sensors=np.int64(n_sensors), d_min=np.float64(d_min), seed=np.int64(seed), gem=piv)
+    print(f"{name}: n={n} r={spr.r} gem sensors={piv} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
 def main():
     sps = _import_reference()
     sys.path.insert(0, ROOT)
     from oracle import synth
     os.makedirs(GOLD, exist_ok=True)
     rng = np.random.default_rng(20261018)
+    gem_only = "--gem-only" in sys.argv         # leaves the committed g1..g5 fixtures untouched
+    if not gem_only:
 
-    # g1: the reference unit tests' own shape (tests/test_rom.py:8-13: 2 features x 10 points x 5)
-    _case(sps, "g1_unit_20x5", rng.random((20, 5)), 2, 4, rng=rng)
-    # g2: random 3 features x 400 cells x 12 snapshots, variance-based rank, pareto scaling
-    _case(sps, "g2_rand_1200x12_pareto", rng.random((1200, 12)) + 0.5, 3, 95.0,
-          select_modes="variance", scale_type="pareto", rng=rng)
-    # g3: synthetic generator, README-like layout (9 features), scaled down: 9 x 400 x 41, r = 14
-    _case(sps, "g3_synth_3600x41_r14", synth.snapshots(9, 400, 41, 14), 9, 14, rng=rng)
-    # g4: range scaling, scalar centring (axis_cnt=None), weighted measurements (sigma != 0)
-    _case(sps, "g4_synth_2400x24_range", synth.snapshots(4, 600, 24, 10), 4, 10,
-          scale_type="range", axis_cnt=None, sigma=0.02, rng=rng)
-    # g5: wider snapshot set, m > 128 exercises the multi-leaf row-mean tree: 2 x 300 x 160, r = 20
-    _case(sps, "g5_synth_600x160_r20", synth.snapshots(2, 300, 160, 20), 2, 20, rng=rng)
+        # g1: the reference unit tests' own shape (tests/test_rom.py:8-13: 2 features x 10 points x 5)
+        _case(sps, "g1_unit_20x5", rng.random((20, 5)), 2, 4, rng=rng)
+        # g2: random 3 features x 400 cells x 12 snapshots, variance-based rank, pareto scaling
+        _case(sps, "g2_rand_1200x12_pareto", rng.random((1200, 12)) + 0.5, 3, 95.0,
+              select_modes="variance", scale_type="pareto", rng=rng)
+        # g3: synthetic generator, README-like layout (9 features), scaled down: 9 x 400 x 41, r = 14
+        _case(sps, "g3_synth_3600x41_r14", synth.snapshots(9, 400, 41, 14), 9, 14, rng=rng)
+        # g4: range scaling, scalar centring (axis_cnt=None), weighted measurements (sigma != 0)
+        _case(sps, "g4_synth_2400x24_range", synth.snapshots(4, 600, 24, 10), 4, 10,
+              scale_type="range", axis_cnt=None, sigma=0.02, rng=rng)
+        # g5: wider snapshot set, m > 128 exercises the multi-leaf row-mean tree: 2 x 300 x 160, r = 20
+        _case(sps, "g5_synth_600x160_r20", synth.snapshots(2, 300, 160, 20), 2, 20, rng=rng)
+    # g6/g7: GEM placement (sparse_sensing.py:586-698) with a user mask, without / with a d_min radius
+    rng2 = np.random.default_rng(7)
+    _gem_case(sps, "g6_gem_900x20_r8", synth.snapshots(3, 300, 20, 8), 3, 8, 6, 0.0, 11, rng2)
+    _gem_case(sps, "g7_gem_1200x24_r10_dmin", synth.snapshots(2, 600, 24, 10), 2, 10, 9, 0.08, 12, rng2)
 
 
 if __name__ == "__main__":

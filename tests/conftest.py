@@ -16,8 +16,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def golden_names(gem=False):
+    """Pipeline fixtures (g1..g5) or, with gem=True, the GEM placement fixtures (g6, g7)."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if ("_gem_" in n) == gem]
 
 
 def load_golden(name):
@@ -37,3 +39,9 @@ def load_golden(name):
 @pytest.fixture(params=golden_names())
 def golden(request):
     return load_golden(request.param)
+
+
+@pytest.fixture(params=golden_names(gem=True))
+def golden_gem(request):
+    z = np.load(os.path.join(GOLDEN_DIR, request.param + ".npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}

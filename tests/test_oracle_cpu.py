@@ -136,3 +136,17 @@ def test_oracle_validation_errors():
         po.choose_rank(ev, 3, "number", 4)
     with pytest.raises(ValueError):
         po.choose_rank(ev, 3, "bogus", 1)
+
+
+# ---- GEM placement: oracle == unmodified reference (sparse_sensing.py:586-698), jitter reproduced
+#      by seeding numpy's global generator exactly like oracle/make_golden.py did -----------------
+def test_gem_oracle_matches_reference_golden(golden_gem):
+    g = golden_gem
+    np.random.seed(int(g["seed"]))
+    sensors, cond = po.gem_placement(g["Ur"], g["xyz"], int(g["F"]), int(g["n_sensors"]), g["mask"], float(g["d_min"]))
+    np.testing.assert_array_equal(sensors, g["gem"])
+    assert np.all(g["mask"][sensors])
+    if float(g["d_min"]) > 0:
+        P = np.tile(g["xyz"], (int(g["F"]), 1))[sensors]
+        D = np.linalg.norm(P[:, None, :] - P[None, :, :], axis=2)
+        assert np.all(D[np.triu_indices(len(sensors), 1)] >= float(g["d_min"]))
