@@ -125,6 +125,20 @@ class ROM:
         self._host = {}
         return self
 
+    @classmethod
+    def from_npy(cls, path, n_features, xyz=None, group=None):
+        """Extension: build from an on-disk .npy snapshot matrix (README.md:50-53), streamed straight
+        into HBM (openmeasure_b200/ingest.py).  One process per GPU: every rank reads only its own
+        cells of every feature; `xyz` are then the coordinates of those cells."""
+        from . import ingest
+        rank, world = 0, 1
+        if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+        if type(n_features) is not int:
+            raise TypeError('The parameter n_features is not an integer.')
+        Xd = ingest.load_npy_shard(path, n_features, rank, world)
+        return cls.from_device(Xd, n_features, xyz, group=group)
+
     def _engine(self):
         if self._eng is None:
             _eng.require_cuda()

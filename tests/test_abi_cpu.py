@@ -104,3 +104,30 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "oracle.clib" not in src and "pod_oracle" not in src, f
+
+
+# ---- ingest: .npy header parsing and shard byte ranges (host logic, no device) -----------------
+def test_npy_shard_ranges(tmp_path):
+    import numpy as np
+    from openmeasure_b200 import ingest
+    X = np.arange(3 * 10 * 4, dtype=np.float64).reshape(30, 4)
+    p = tmp_path / "X.npy"
+    np.save(p, X)
+    shape, off = ingest.npy_header(str(p))
+    assert shape == (30, 4)
+    raw = open(p, "rb").read()
+    got = []
+    for rank in range(3):
+        ranges, ncl = ingest.shard_ranges(shape, off, 3, rank, 3)
+        c0, ncl2 = ingest.shard_cells(10, rank, 3)
+        assert ncl == ncl2
+        rows = np.concatenate([np.frombuffer(raw[o:o + nb], dtype=np.float64).reshape(-1, 4) for o, nb, _ in ranges])
+        np.testing.assert_array_equal(rows, np.concatenate([X[f * 10 + c0: f * 10 + c0 + ncl] for f in range(3)]))
+        got.append(ncl)
+    assert sum(got) == 10 and got == [4, 3, 3]
+    np.save(p, X.astype(np.float32))
+    with pytest.raises(ValueError):
+        ingest.npy_header(str(p))
+    np.save(p, np.asfortranarray(X))
+    with pytest.raises(ValueError):
+        ingest.npy_header(str(p))

@@ -568,3 +568,26 @@ def test_reconstruct_with_sampling(torch_cuda, kind):
                                rtol=1e-13)
     if kind == "onehot":                                  # consistent with sampling the full reconstruction
         np.testing.assert_allclose(got, spr.reconstruct(Ar)[rows], rtol=RTOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# ingest: .npy snapshot file -> HBM shard (pinned ring + copy stream), then the same pipeline
+# ---------------------------------------------------------------------------------------------
+def test_npy_ingest_roundtrip_and_fit(torch_cuda, tmp_path):
+    from openmeasure_b200 import ingest
+    from oracle import pod_oracle as po, synth as osynth
+    F, n_c, m, r = 3, 4001, 24, 10
+    X = osynth.snapshots(F, n_c, m, r)
+    path = str(tmp_path / "X_train.npy")
+    np.save(path, X)
+    for world in (1, 3):
+        parts = [ingest.load_npy_shard(path, F, rk, world, chunk_bytes=100_000).cpu().numpy() for rk in range(world)]
+        for rk, P in enumerate(parts):
+            c0, ncl = ingest.shard_cells(n_c, rk, world)
+            np.testing.assert_array_equal(P, np.concatenate([X[f * n_c + c0: f * n_c + c0 + ncl] for f in range(F)]))
+    spr = _sps().SPR.from_npy(path, F, np.zeros((n_c, 3)), group=False)
+    spr.fit(select_modes="number", n_modes=r)
+    spr.optimal_placement()
+    ref = po.placement_pipeline(X, F, r)
+    np.testing.assert_array_equal(spr.X_cnt, ref["X_cnt"])
+    np.testing.assert_array_equal(spr.qr_pivots, ref["piv"])
