@@ -70,19 +70,21 @@ __device__ __forceinline__ bool cand_better(double b1, int64_t k1, double b2, in
 {
     return b1 > b2 || (b1 == b2 && k1 < k2);
 }
+// compare-select max: the norms are never NaN (fmax costs ~10 instructions in FP64 for its NaN rules)
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ void cand_merge(Cand& a, const Cand& b)
 {
     if (cand_better(b.best, b.key, a.best, a.key)) {
-        double s = fmax(a.best, b.second);
+        double s = dmax(a.best, b.second);
         a.best = b.best; a.idx = b.idx; a.key = b.key; a.second = s;
     } else {
-        a.second = fmax(a.second, b.best);
+        a.second = dmax(a.second, b.best);
     }
 }
 __device__ __forceinline__ void cand_push(Cand& a, double v, int64_t idx, int64_t key)
 {
     if (cand_better(v, key, a.best, a.key)) { a.second = a.best; a.best = v; a.idx = idx; a.key = key; }
-    else a.second = fmax(a.second, v);
+    else a.second = dmax(a.second, v);
 }
 // push with the LAPACK position key computed only when it can matter (v >= current best)
 __device__ __forceinline__ void cand_push_lazy(Cand& a, double v, int64_t j, const Shard& sh, const Panel* P,
@@ -93,7 +95,7 @@ __device__ __forceinline__ void cand_push_lazy(Cand& a, double v, int64_t j, con
         const int64_t key = g < s_total ? P->posmap[g] : g;
         cand_push(a, v, j, key);
     } else {
-        a.second = fmax(a.second, v);
+        a.second = dmax(a.second, v);
     }
 }
 __device__ __forceinline__ Cand cand_shfl_xor(const Cand& a, int o)
@@ -631,6 +633,11 @@ qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, cons
     }
 }
 
+// The panel is pure latency (one CTA between two grid-wide passes), so it is organised around
+// dependent-chain length, not work: every load a thread needs is issued before the first use, the
+// candidate records are merged by a shuffle tree, and after the pivot column has arrived a single
+// warp does the reflector algebra -- the t <= 8 dot products of a step run side by side on the 8
+// quads of the warp (4 lanes x L/4 elements each), the tiny triangular products on one lane per row.
 template <bool MULTI>
 __global__ void __launch_bounds__(PN_THREADS)
 qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand, const double* __restrict__ src,
@@ -640,34 +647,50 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
 {
     __shared__ Cand s_c[PN_THREADS / 32];
     __shared__ double s_V[QR_BMAX][QR_RMAX];   // earlier reflectors of this block (rows < t), then v_t
-    __shared__ double s_T[QR_BMAX][QR_BMAX];
+    __shared__ double s_T[QR_BMAX][QR_BMAX + 1];
     __shared__ double s_x[QR_RMAX];            // pivot column tail over rows i0..
-    __shared__ double s_z[QR_BMAX];
-    __shared__ double s_red[PN_THREADS / 32];
-    __shared__ int64_t s_p;
-    __shared__ double s_tau, s_scal;
+    __shared__ double s_z[QR_BMAX], s_g[QR_BMAX];
+    __shared__ int64_t s_win[4];               // winner: global index, LAPACK key, local column, gap bits
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // 0. block state -> shared memory (independent of the pivot: overlaps the argmax reduction)
-    for (int e = threadIdx.x; e < t * L; e += PN_THREADS) {
-        const int a = e / L, k = e - a * L;
-        s_V[a][k] = P->V[a][k];
-    }
-    for (int e = threadIdx.x; e < t * t; e += PN_THREADS) {
-        const int a = e / t, b = e - a * t;
-        s_T[a][b] = P->T[a][b];
+    for (int a = warp; a < t; a += PN_THREADS / 32)
+        for (int k = lane; k < L; k += 32) s_V[a][k] = P->V[a][k];
+    if (threadIdx.x < QR_BMAX * QR_BMAX) {
+        const int a = threadIdx.x >> 3, b = threadIdx.x & 7;
+        s_T[a][b] = (a <= b && b < t) ? P->T[a][b] : 0.0;      // upper triangular; the rest of P->T is never written
     }
 
     Cand c = cand_empty();       // winner: idx = GLOBAL row index, key = LAPACK position
     int64_t p_local = -1;        // the winner's local column, -1 if another rank owns it
     if (!MULTI) {
-        // 1. global argmax over the pass kernel's records
-        for (int e = threadIdx.x; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
-        c = cand_block_reduce(c, s_c);
-        if (threadIdx.x == 0) s_p = c.idx;
+        // 1. global argmax over the pass kernel's records: all loads first, then the merges
+        constexpr int NR = 5;
+        Cand rc[NR];
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+            const int e = threadIdx.x + u * PN_THREADS;
+            rc[u] = cand_empty();
+            if (e < ncand) {
+                const double2 lo = *reinterpret_cast<const double2*>(&cand[e].best);
+                const longlong2 hi = *reinterpret_cast<const longlong2*>(&cand[e].idx);
+                rc[u].best = lo.x; rc[u].second = lo.y; rc[u].idx = hi.x; rc[u].key = hi.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NR; ++u) cand_merge(c, rc[u]);
+        for (int e = threadIdx.x + NR * PN_THREADS; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { Cand b = cand_shfl_xor(c, o); cand_merge(c, b); }
+        if (lane == 0) s_c[warp] = c;
         __syncthreads();
-        p_local = s_p;
-        // 2. pivot column tail at block start
+        c = (lane < PN_THREADS / 32) ? s_c[lane] : cand_empty();
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { Cand b = cand_shfl_xor(c, o); cand_merge(c, b); }
+        c.best = __shfl_sync(0xFFFFFFFFu, c.best, 0); c.second = __shfl_sync(0xFFFFFFFFu, c.second, 0);
+        c.idx = __shfl_sync(0xFFFFFFFFu, c.idx, 0); c.key = __shfl_sync(0xFFFFFFFFu, c.key, 0);
+        p_local = c.idx;
+        // 2. pivot column tail at block start (every warp knows the winner: no second barrier)
         const double* col = src + basis_index(i0, p_local, r);
         for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = col[(int64_t)k * OMB_TB];
     } else {
@@ -680,145 +703,149 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
             recs = p2p_rec(pp.mine, sh.world, i & 1, 0);
         }
         // 1. winner among the ranks' records (fixed order: identical decision on every rank)
-        if (threadIdx.x == 0) {
-            int wr = -1;
-            for (int g = 0; g < sh.world; ++g) {
-                const double* rc = recs + (int64_t)g * QR_REC;
-                Cand b;
-                b.best = __ldcg(rc + 0); b.second = __ldcg(rc + 1);
-                b.key = __double_as_longlong(__ldcg(rc + 2)); b.idx = __double_as_longlong(__ldcg(rc + 3));
-                if (b.idx < 0) continue;
-                const bool wins = cand_better(b.best, b.key, c.best, c.key);
-                cand_merge(c, b);
-                if (wins) { wr = g; p_local = (g == sh.rank) ? __double_as_longlong(__ldcg(rc + 4)) : -1; }
-            }
-            s_p = wr;
+        int wr = -1;
+        for (int g = 0; g < sh.world; ++g) {
+            const double* rcp = recs + (int64_t)g * QR_REC;
+            Cand b;
+            b.best = __ldcg(rcp + 0); b.second = __ldcg(rcp + 1);
+            b.key = __double_as_longlong(__ldcg(rcp + 2)); b.idx = __double_as_longlong(__ldcg(rcp + 3));
+            if (b.idx < 0) continue;
+            const bool wins = cand_better(b.best, b.key, c.best, c.key);
+            cand_merge(c, b);
+            if (wins) { wr = g; p_local = (g == sh.rank) ? __double_as_longlong(__ldcg(rcp + 4)) : -1; }
         }
-        __syncthreads();
-        const double* rc = recs + (int64_t)s_p * QR_REC + 8;
-        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = __ldcg(rc + k);
+        const double* rcw = recs + (int64_t)(wr < 0 ? 0 : wr) * QR_REC + 8;
+        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = __ldcg(rcw + k);
     }
-    if (threadIdx.x == 0) {
-        const int64_t p = c.idx;         // global row index (single rank: local == global)
+    if (threadIdx.x == 32) {
+        s_win[0] = c.idx; s_win[1] = c.key; s_win[2] = p_local;
+        s_win[3] = __double_as_longlong((c.second < 0.0 || c.best <= 0.0) ? 1.0 : (c.best - c.second) / c.best);
+    }
+    __syncthreads();                     // s_x, s_V, s_T complete
+    if (warp == 1 && lane == 0) {
+        // LAPACK's swap of positions i <-> pos(p) beside the reflector arithmetic of warp 0
+        const int64_t p = s_win[0], pos_p = s_win[1], pl = s_win[2];
         piv[i] = p + index_base;
-        gap[i] = (c.second < 0.0 || c.best <= 0.0) ? 1.0 : (c.best - c.second) / c.best;
-        // LAPACK's swap of positions i <-> pos(p): the column sitting at position i moves to pos(p)
-        const int64_t pos_p = c.key;
+        gap[i] = __longlong_as_double(s_win[3]);
         if (pos_p != i) {
-            const int64_t ci = P->col_at_pos[i];
+            const int64_t ci = P->col_at_pos[i];       // the column sitting at position i moves to pos(p)
             P->posmap[ci] = pos_p;
             if (pos_p < s_total) P->col_at_pos[pos_p] = ci;
         }
         P->col_at_pos[i] = p;
         if (p < s_total) P->posmap[p] = i;
-        if (p_local >= 0) vn1[p_local] = -1.0;     // never a candidate again
+        if (pl >= 0) vn1[pl] = -1.0;     // never a candidate again
     }
-    __syncthreads();
+    if (warp != 0) return;
+
+    const int qd = lane >> 2, ql = lane & 3;          // quad qd handles reflector qd in the dot products
+    constexpr int NK = QR_RMAX / 32;
+    // dots[qd] = V[qd] . y  for the 8 reflectors at once (rows beyond t hold zeros in s_T, so the
+    // results of quads >= t are never used)
+    auto quad_dots = [&](const double* y) {
+        double a0 = 0.0, a1 = 0.0;
+        if (qd < t) {
+            const double* vq = s_V[qd];
+            int k = ql;
+            for (; k + 4 < L; k += 8) { a0 = fma(vq[k], y[k], a0); a1 = fma(vq[k + 4], y[k + 4], a1); }
+            if (k < L) a0 = fma(vq[k], y[k], a0);
+        }
+        double sacc = a0 + a1;
+        sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 1);
+        sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 2);
+        return sacc;
+    };
+
     if (t > 0) {
         // x <- Q^T x = x - V (T^T (V^T x))   (compact WY of the block's earlier reflectors)
-        for (int tt = warp; tt < t; tt += PN_THREADS / 32) {
-            double sacc = 0.0;
-            for (int k = lane; k < L; k += 32) sacc = fma(s_V[tt][k], s_x[k], sacc);
+        const double zq = quad_dots(s_x);
+        if (ql == 0) s_z[qd] = qd < t ? zq : 0.0;
+        __syncwarp();
+        if (lane < QR_BMAX) {
+            double zz = 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, o);
-            if (lane == 0) s_z[tt] = sacc;
+            for (int b = 0; b < QR_BMAX; ++b) zz = fma(s_T[b][lane], s_z[b], zz);      // (T^T z)_lane; T is upper triangular
+            s_g[lane] = lane < t ? zz : 0.0;
         }
-        __syncthreads();
-        double zz = 0.0;
-        if (threadIdx.x < t) {
-            const int a = threadIdx.x;
-            for (int b = 0; b <= a; ++b) zz = fma(s_T[b][a], s_z[b], zz);      // (T^T z)_a
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < NK; ++u) {
+            const int k = lane + 32 * u;
+            if (k < L) {
+                double xv = s_x[k];
+                for (int a = 0; a < t; ++a) xv = fma(-s_V[a][k], s_g[a], xv);
+                s_x[k] = xv;
+            }
         }
-        __syncthreads();
-        if (threadIdx.x < t) s_z[threadIdx.x] = zz;
-        __syncthreads();
-        for (int k = threadIdx.x; k < L; k += PN_THREADS) {
-            double x = s_x[k];
-            for (int a = 0; a < t; ++a) x = fma(-s_V[a][k], s_z[a], x);
-            s_x[k] = x;
-        }
-        __syncthreads();
+        __syncwarp();
     }
 
     // 3. dlarfg on x[t:]  (alpha = x[t], tail x[t+1:])
     double xn2;
     if (seq_norm) {
-        if (threadIdx.x == 0) {
-            double sacc = 0.0;
-            for (int k = t + 1; k < L; ++k) sacc = fma(s_x[k], s_x[k], sacc);
-            s_red[0] = sacc;
-        }
-        __syncthreads();
-        xn2 = s_red[0];
-        __syncthreads();
+        // dnrm2's order (block == 1: bit-identical to dlaqp2): one lane sums the tail sequentially
+        double sacc = 0.0;
+        if (lane == 0) for (int k = t + 1; k < L; ++k) sacc = fma(s_x[k], s_x[k], sacc);
+        xn2 = __shfl_sync(0xFFFFFFFFu, sacc, 0);
     } else {
         double sacc = 0.0;
-        for (int k = t + 1 + threadIdx.x; k < L; k += PN_THREADS) sacc = fma(s_x[k], s_x[k], sacc);
-        xn2 = block_sum(sacc, s_red);
+        for (int k = t + 1 + lane; k < L; k += 32) sacc = fma(s_x[k], s_x[k], sacc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, o);
+        xn2 = sacc;
     }
-    if (threadIdx.x == 0) {
-        const double alpha = s_x[t];
+    const double alpha = s_x[t];
+    double beta = alpha, tau = 0.0, scal = 0.0;
+    {
         const double xnorm = sqrt(xn2);
-        double beta = alpha, tau = 0.0, scal = 0.0;
         if (L - t > 1 && xnorm != 0.0) {
             // dlapy2(alpha, xnorm)
             const double xa = fabs(alpha), ya = xnorm;
-            const double w = fmax(xa, ya), z = fmin(xa, ya);
+            const double w = xa > ya ? xa : ya, zmin = xa > ya ? ya : xa;
             double h = w;
-            if (z != 0.0) { const double qq = z / w; h = w * sqrt(1.0 + qq * qq); }
+            if (zmin != 0.0) { const double qq = zmin / w; h = w * sqrt(1.0 + qq * qq); }
             beta = -copysign(h, alpha);
             tau = (beta - alpha) / beta;
             scal = 1.0 / (alpha - beta);
         }
-        s_tau = tau; s_scal = scal;
-        rdiag[i] = beta;
-        P->tau[t] = tau;
     }
-    __syncthreads();
-    const double tau = s_tau, scal = s_scal;
-    for (int k = threadIdx.x; k < L; k += PN_THREADS) {
-        double v = 0.0;
-        if (k == t) v = 1.0;
-        else if (k > t) v = (tau != 0.0) ? s_x[k] * scal : 0.0;
-        P->V[t][k] = v;
-        s_V[t][k] = v;
+    if (lane == 0) { rdiag[i] = beta; P->tau[t] = tau; }
+    for (int k = lane; k < L; k += 32) {
+        double vv = 0.0;
+        if (k == t) vv = 1.0;
+        else if (k > t) vv = (tau != 0.0) ? s_x[k] * scal : 0.0;
+        P->V[t][k] = vv;
+        s_V[t][k] = vv;
     }
-    __syncthreads();
+    __syncwarp();
 
     // 4. compact-WY column t of T, and q = Q e_t = e_t - V T (V^T e_t)
-    for (int tt = warp; tt < t; tt += PN_THREADS / 32) {
-        double sacc = 0.0;
-        for (int k = lane; k < L; k += 32) sacc = fma(s_V[tt][k], s_V[t][k], sacc);     // V[:, tt]^T v_t
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, o);
-        if (lane == 0) s_z[tt] = sacc;
-    }
-    __syncthreads();
-    if (threadIdx.x <= t) {
+    const double zv = quad_dots(s_V[t]);               // V[:, qd]^T v_t
+    if (ql == 0) s_z[qd] = qd < t ? zv : 0.0;
+    __syncwarp();
+    if (lane < QR_BMAX) {
         // T[0:t, t] = -tau * T[0:t, 0:t] * (V^T v_t);  T[t][t] = tau
-        const int a = threadIdx.x;
-        double val = tau;
-        if (a < t) {
+        double val = 0.0;
+        if (lane < t) {
             double sacc = 0.0;
-            for (int b = a; b < t; ++b) sacc = fma(s_T[a][b], s_z[b], sacc);
+            for (int b = lane; b < t; ++b) sacc = fma(s_T[lane][b], s_z[b], sacc);
             val = -tau * sacc;
+        } else if (lane == t) {
+            val = tau;
         }
-        s_T[a][t] = val;
-        P->T[a][t] = val;
+        if (lane <= t) { s_T[lane][t] = val; P->T[lane][t] = val; }
     }
-    __syncthreads();
-    double g = 0.0;
-    if (threadIdx.x <= t) {
+    __syncwarp();
+    if (lane < QR_BMAX) {
         // g = T * (V^T e_t),  (V^T e_t)_b = V[b][t]
-        const int a = threadIdx.x;
-        for (int b = a; b <= t; ++b) g = fma(s_T[a][b], s_V[b][t], g);
+        double gv = 0.0;
+        if (lane <= t) for (int b = lane; b <= t; ++b) gv = fma(s_T[lane][b], s_V[b][t], gv);
+        s_g[lane] = gv;
     }
-    __syncthreads();
-    if (threadIdx.x <= t) s_z[threadIdx.x] = g;
-    __syncthreads();
-    for (int k = threadIdx.x; k < L; k += PN_THREADS) {
+    __syncwarp();
+    for (int k = lane; k < L; k += 32) {
         double qv = (k == t) ? 1.0 : 0.0;
-        for (int a = 0; a <= t; ++a) qv = fma(-s_V[a][k], s_z[a], qv);
+        for (int a = 0; a <= t; ++a) qv = fma(-s_V[a][k], s_g[a], qv);
         P->q[k] = qv;
     }
 }
