@@ -54,20 +54,42 @@ __device__ __forceinline__ void jacobi_rot(double apq, double app, double aqq, d
     big = rel2 > 1.0e-18 * den && fabs(apq) > big_abs;
 }
 
-// Two barriers per step: (1) lanes 0..npair-1 of warp 0 compute the step's rotations, (2) every
-// thread applies them to its fixed work items (no index arithmetic inside the sweeps):
-//   e <  npair^2 : block (pair i rows) x (pair j columns) of  A <- J^T A J
-//   e >= npair^2 : two rows of  V <- V J  for one pair
+// the 2 x 2 block (rows p_i, q_i) x (columns p_j, q_j) of  J^T A J  for the rotations (ci, si), (cj, sj)
+struct Blk { double b00, b01, b10, b11; };
+__device__ __forceinline__ Blk jacobi_block(const double* __restrict__ A, int pi, int qi, int pj, int qj, double ci,
+                                            double si, double cj, double sj)
+{
+    const double a00 = A[pi * EJ_LD + pj], a01 = A[pi * EJ_LD + qj];
+    const double a10 = A[qi * EJ_LD + pj], a11 = A[qi * EJ_LD + qj];
+    // columns (J_j), then rows (J_i^T)
+    const double b00 = cj * a00 - sj * a01, b01 = sj * a00 + cj * a01;
+    const double b10 = cj * a10 - sj * a11, b11 = sj * a10 + cj * a11;
+    Blk o;
+    o.b00 = ci * b00 - si * b10; o.b01 = ci * b01 - si * b11;
+    o.b10 = si * b00 + ci * b10; o.b11 = si * b01 + ci * b11;
+    return o;
+}
+
+// ONE barrier per step.  While every thread applies the step's rotations to its fixed work items
+//   e <  npair^2 : block (pair i rows) x (pair j columns) of  A <- J^T A J   (A is ping-ponged between
+//                  two shared-memory copies: the blocks of a step tile the whole matrix)
+//   e >= npair^2 : two rows of  V <- V J  for one pair                       (single owner: in place)
+// npair look-ahead threads (the last ones of the CTA, idle otherwise) each re-derive the three entries
+// a_pq, a_pp, a_qq their pair of the NEXT step will see -- the same expressions, hence the same bits,
+// as the owners of those blocks compute -- and from them the next rotation.  The rotation chain
+// (~1000 cycles of dependent arithmetic) thereby runs beside the update instead of after it.
 __global__ void __launch_bounds__(EJ_THREADS)
 eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_out, double* __restrict__ V_out,
                    int* __restrict__ info)
 {
     extern __shared__ double sm[];
-    double* A = sm;                           // [EJ_MAX][EJ_LD]
-    double* V = sm + EJ_MAX * EJ_LD;          // [EJ_MAX][EJ_LD]
-    __shared__ double s_c[EJ_MAX / 2], s_s[EJ_MAX / 2];
+    double* A0 = sm;                          // [EJ_MAX][EJ_LD]
+    double* A1 = sm + EJ_MAX * EJ_LD;         // [EJ_MAX][EJ_LD]
+    double* V = sm + 2 * EJ_MAX * EJ_LD;      // [EJ_MAX][EJ_LD]
+    __shared__ double s_c[2][EJ_MAX / 2], s_s[2][EJ_MAX / 2];
     __shared__ int s_order[EJ_MAX];
     __shared__ unsigned short s_sched[(EJ_MAX - 1) * (EJ_MAX / 2)];
+    __shared__ unsigned char s_slot[(EJ_MAX - 1) * EJ_MAX];    // step, index -> pair * 2 + (index is the pair's q)
 
     const int M = (m + 1) & ~1;             // even number of players; index m (if any) is a dummy
     const int npair = M / 2;
@@ -77,7 +99,7 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
         // dummy player of an odd m is a zero row/column that only ever meets identity rotations
         double a = 0.0;
         if (i < m && j < m) a = (i <= j) ? G[i * m + j] : G[j * m + i];
-        A[i * EJ_LD + j] = a;
+        A0[i * EJ_LD + j] = a;
         V[i * EJ_LD + j] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
@@ -87,7 +109,7 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
     __shared__ double s_floor;
     if (threadIdx.x == 0) {
         double dmax = 0.0;
-        for (int i = 0; i < m; ++i) dmax = fmax(dmax, fabs(A[i * EJ_LD + i]));
+        for (int i = 0; i < m; ++i) dmax = fmax(dmax, fabs(A0[i * EJ_LD + i]));
         s_floor = dmax * 1.0e-20;
     }
     // round-robin schedule: pair i of step k, stored once (no integer division in the sweeps)
@@ -98,6 +120,8 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
         else { p = (step + i) % (M - 1); q = (step - i + (M - 1)) % (M - 1); }
         if (p > q) { const int tswap = p; p = q; q = tswap; }
         s_sched[e] = (unsigned short)((p << 8) | q);
+        s_slot[step * M + p] = (unsigned char)(2 * i);
+        s_slot[step * M + q] = (unsigned char)(2 * i + 1);
     }
     __syncthreads();
     const double floor_abs = s_floor, big_abs = s_floor * 1.0e7;      // 1e-13 * max|a_ii|
@@ -111,47 +135,57 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
         if (e < nblk) { it_i[k] = e / npair; it_j[k] = e - it_i[k] * npair; }
         else if (e < nitem) { const int u = e - nblk; it_j[k] = u / npair; it_i[k] = npair + (u - it_j[k] * npair); }
     }
+    const int la = EJ_THREADS - 1 - (int)threadIdx.x;                // look-ahead pair of this thread (if < npair)
 
-    int sweep = 0;
+    // rotations of the very first step
+    if (la < npair) {
+        const int p = s_sched[la] >> 8, q = s_sched[la] & 255;
+        double c = 1.0, s = 0.0;
+        bool big = false;
+        if (q < m) jacobi_rot(A0[p * EJ_LD + q], A0[p * EJ_LD + p], A0[q * EJ_LD + q], floor_abs, big_abs, c, s, big);
+        s_c[0][la] = c; s_s[0][la] = s;
+    }
+    __syncthreads();
+
+    double* Ain = A0;
+    double* Aout = A1;
+    int sweep = 0, par = 0;
+    int big_next = 0;            // a big rotation among those prepared for the coming step (uniform)
+    {
+        // the first step's own "big" flags: recompute cheaply from its rotations being non-trivial is not
+        // equivalent, so evaluate the criterion once more for step 0 (only here, outside the loop)
+        int b0 = 0;
+        if (la < npair) {
+            const int p = s_sched[la] >> 8, q = s_sched[la] & 255;
+            if (q < m) {
+                const double apq = A0[p * EJ_LD + q], den = fabs(A0[p * EJ_LD + p] * A0[q * EJ_LD + q]);
+                b0 = (apq * apq > 1.0e-18 * den && fabs(apq) > big_abs) ? 1 : 0;
+            }
+        }
+        big_next = __syncthreads_or(b0);
+    }
     for (; sweep < EJ_MAX_SWEEPS; ++sweep) {
         int sweep_big = 0;
         for (int step = 0; step < M - 1; ++step) {
+            sweep_big |= big_next;
             const unsigned short* sched = s_sched + step * npair;
-            int my_big = 0;
-            // 1. the M/2 disjoint pairs of this step and their rotations
-            if (threadIdx.x < npair) {
-                const int p = sched[threadIdx.x] >> 8, q = sched[threadIdx.x] & 255;
-                double c = 1.0, s = 0.0;
-                bool big = false;
-                if (q < m) jacobi_rot(A[p * EJ_LD + q], A[p * EJ_LD + p], A[q * EJ_LD + q], floor_abs, big_abs, c, s, big);
-                s_c[threadIdx.x] = c; s_s[threadIdx.x] = s;
-                my_big = big ? 1 : 0;
-            }
-            __syncthreads();
-            // 2. A <- J^T A J by 2 x 2 blocks, V <- V J by column pairs (every entry has one owner)
+            const double* cc = s_c[par];
+            const double* ss = s_s[par];
+            // 1. apply this step's rotations
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (it_i[k] < 0) continue;
                 if (it_i[k] < npair) {
                     const int i = it_i[k], j = it_j[k];
-                    const double si = s_s[i], sj = s_s[j];
-                    if (si == 0.0 && sj == 0.0) continue;
-                    const double ci = s_c[i], cj = s_c[j];
                     const int pi = sched[i] >> 8, qi = sched[i] & 255, pj = sched[j] >> 8, qj = sched[j] & 255;
-                    const double a00 = A[pi * EJ_LD + pj], a01 = A[pi * EJ_LD + qj];
-                    const double a10 = A[qi * EJ_LD + pj], a11 = A[qi * EJ_LD + qj];
-                    // columns (J_j), then rows (J_i^T)
-                    const double b00 = cj * a00 - sj * a01, b01 = sj * a00 + cj * a01;
-                    const double b10 = cj * a10 - sj * a11, b11 = sj * a10 + cj * a11;
-                    A[pi * EJ_LD + pj] = ci * b00 - si * b10;
-                    A[pi * EJ_LD + qj] = ci * b01 - si * b11;
-                    A[qi * EJ_LD + pj] = si * b00 + ci * b10;
-                    A[qi * EJ_LD + qj] = si * b01 + ci * b11;
+                    const Blk o = jacobi_block(Ain, pi, qi, pj, qj, cc[i], ss[i], cc[j], ss[j]);
+                    Aout[pi * EJ_LD + pj] = o.b00; Aout[pi * EJ_LD + qj] = o.b01;
+                    Aout[qi * EJ_LD + pj] = o.b10; Aout[qi * EJ_LD + qj] = o.b11;
                 } else {
                     const int i = it_i[k] - npair, r0 = 2 * it_j[k];
-                    const double s = s_s[i];
+                    const double s = ss[i];
                     if (s != 0.0) {
-                        const double c = s_c[i];
+                        const double c = cc[i];
                         const int p = sched[i] >> 8, q = sched[i] & 255;
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
@@ -163,11 +197,37 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
                     }
                 }
             }
-            sweep_big |= __syncthreads_or(my_big);
+            // 2. look-ahead: the rotation of pair `la` of the NEXT step from the entries it will see
+            int my_big = 0;
+            if (la < npair) {
+                const int nstep = (step + 1 == M - 1) ? 0 : step + 1;
+                const unsigned short pq = s_sched[nstep * npair + la];
+                const int p = pq >> 8, q = pq & 255;
+                double c = 1.0, s = 0.0;
+                bool big = false;
+                if (q < m) {
+                    const unsigned char* slot = s_slot + step * M;
+                    const int ip = slot[p] >> 1, rp = slot[p] & 1, iq = slot[q] >> 1, rq = slot[q] & 1;
+                    const int ppi = sched[ip] >> 8, qpi = sched[ip] & 255, ppq = sched[iq] >> 8, qpq = sched[iq] & 255;
+                    const double cip = cc[ip], sip = ss[ip], ciq = cc[iq], siq = ss[iq];
+                    const Blk bpq = jacobi_block(Ain, ppi, qpi, ppq, qpq, cip, sip, ciq, siq);
+                    const Blk bpp = jacobi_block(Ain, ppi, qpi, ppi, qpi, cip, sip, cip, sip);
+                    const Blk bqq = jacobi_block(Ain, ppq, qpq, ppq, qpq, ciq, siq, ciq, siq);
+                    const double apq = rp ? (rq ? bpq.b11 : bpq.b10) : (rq ? bpq.b01 : bpq.b00);
+                    const double app = rp ? bpp.b11 : bpp.b00;
+                    const double aqq = rq ? bqq.b11 : bqq.b00;
+                    jacobi_rot(apq, app, aqq, floor_abs, big_abs, c, s, big);
+                }
+                s_c[par ^ 1][la] = c; s_s[par ^ 1][la] = s;
+                my_big = big ? 1 : 0;
+            }
+            big_next = __syncthreads_or(my_big);
+            double* tsw = Ain; Ain = Aout; Aout = tsw;
+            par ^= 1;
         }
         if (!sweep_big) break;
     }
-
+    const double* A = Ain;
 
     // descending order by rank counting (ties broken by index)
     if (threadIdx.x < m) {
@@ -210,7 +270,7 @@ extern "C" int omb_eigh_jacobi(const double* d_G, int64_t m, double* d_w, double
     using namespace omb;
     OMB_CHECK_ARG(d_G && d_w && d_V, "null pointer");
     OMB_CHECK_ARG(m >= 1 && m <= EJ_MAX, "m must be in [1, 64]");
-    const size_t smem = sizeof(double) * 2 * EJ_MAX * EJ_LD;
+    const size_t smem = sizeof(double) * 3 * EJ_MAX * EJ_LD;
     OMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eigh_jacobi_kernel<<<1, EJ_THREADS, smem, (cudaStream_t)stream>>>(d_G, (int)m, d_w, d_V, d_info);
     return check_launch("eigh_jacobi_kernel");

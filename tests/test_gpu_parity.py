@@ -591,3 +591,54 @@ def test_npy_ingest_roundtrip_and_fit(torch_cuda, tmp_path):
     ref = po.placement_pipeline(X, F, r)
     np.testing.assert_array_equal(spr.X_cnt, ref["X_cnt"])
     np.testing.assert_array_equal(spr.qr_pivots, ref["piv"])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes (configs[1]: 1.65M x 41, r = 40; configs[2]: 16.2M x 256, r = 100, one
+# GPU's worth of HBM): size-independent properties, everything checked on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,n_c,m,r", [(9, 183620, 41, 40), (9, 1800000, 256, 100)])
+def test_full_size_properties(torch_cuda, F, n_c, m, r):
+    from openmeasure_b200 import synth as gsynth
+    torch = torch_cuda
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 * F * n_c * m * 8 // 4:
+        pytest.skip("not enough free HBM for this configuration")
+    Xd = gsynth.snapshots(F, n_c, m, r)
+    spr = _sps().SPR.from_device(Xd, F)
+    spr.fit(select_modes='number', n_modes=r)
+    eng = spr._eng
+    n = F * n_c
+    U = eng.basis_rows()
+    # (1) orthonormal modes, (2) the POD identity  X0^T U = V Sigma  column by column (X0 never materialised:
+    #     X0^T U = (X^T (U / scl_row) - ones * cnt^T (U / scl_row)))
+    G = U.T @ U
+    assert float((G - torch.eye(r, dtype=torch.float64, device=G.device)).abs().max()) < 1e-9
+    scl_rows = torch.repeat_interleave(eng.scl, eng.n_c_loc)
+    Us = U / scl_rows[:, None]
+    B = Xd.T @ Us - torch.outer(torch.ones(m, dtype=torch.float64, device=U.device), eng.cnt @ Us)
+    S = torch.from_numpy(spr.Sigma_r).to(U.device)
+    Vr = torch.from_numpy(spr.Vr).to(U.device)
+    assert float((B - Vr * S).abs().max() / S[0]) < 1e-9
+    assert bool((S[:-1] >= S[1:]).all()) and spr.pod_rel_err_bound < 1e-10
+    del Us, B, G
+    # (3) placement: the blocked schedule picks the pivots of the unblocked (dlaqp2-bitwise) one, all distinct
+    C = spr.optimal_placement(block=8)
+    piv8 = spr.qr_pivots.copy()
+    gap8 = float(spr.qr_gap.min())
+    spr.optimal_placement(block=1)
+    np.testing.assert_array_equal(piv8, spr.qr_pivots)
+    assert len(set(piv8.tolist())) == r and gap8 > 1e-9 and piv8.min() >= 0 and piv8.max() < n
+    # (4) sample -> predict -> reconstruct round trip on a field that lies in span(Ur): exact recovery
+    spr.train(C)
+    a_true = torch.linspace(-1.0, 1.0, r, dtype=torch.float64, device=U.device)
+    x = scl_rows * (U @ a_true) + eng.cnt
+    pv = torch.from_numpy(piv8).to(U.device)
+    y = np.zeros((r, 3))
+    y[:, 0] = x[pv].cpu().numpy()
+    y[:, 2] = piv8 // n_c
+    a, _ = spr.predict(y)
+    np.testing.assert_allclose(a[0], a_true.cpu().numpy(), rtol=0, atol=1e-7)
+    del U
+    xr = eng.reconstruct(torch.from_numpy(a).to(Xd.device))[:, 0]
+    assert float((xr - x).abs().max() / x.abs().max()) < 1e-8
