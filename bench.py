@@ -247,25 +247,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
+    # the sampler starts BEFORE the warm-up: the first NVML queries of a process take milliseconds inside
+    # the driver and stall kernel launches (measured: one 10 ms step right after the sampler's first poll)
     clocks = Clocks(local_rank) if rank == 0 and not os.environ.get("OMB_BENCH_NO_CLOCKS") else None
     if clocks:
         clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
     L.omb_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t_wall0 = time.perf_counter()
     e0.record()
+    step_marks = [e0]
     for _ in range(args.steps):
         spr, C = step(timed_qr=True)
+        mk = torch.cuda.Event(enable_timing=True)
+        mk.record()
+        step_marks.append(mk)
     e1.record()
     sync_all()
     t_wall1 = time.perf_counter()
     launches = int(L.omb_launch_count())
     ms = e0.elapsed_time(e1)
     qr_ms = [a.elapsed_time(b) for a, b in qr_events]
+    step_ms = [step_marks[k].elapsed_time(step_marks[k + 1]) for k in range(len(step_marks) - 1)]
     if world > 1:
         tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -410,7 +417,7 @@ def main():
                        "l2": "inputs (%.0f MB per GPU) exceed the 126 MB L2" % (8.0 * n_loc * m / 1e6),
                        "parallelism": "cells sharded over %d rank(s)" % world},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "stages_ms": stages, "reconstruct": recon,
+            "stages_ms": stages, "step_ms": [round(v, 3) for v in step_ms], "reconstruct": recon,
             "pivots_head": [int(p) for p in spr.qr_pivots[:8]], "min_pivot_gap": float(spr.qr_gap.min()),
             "sigma_r_over_sigma_1": float(spr.Sigma_r[-1] / spr.Sigma_r[0]),
         }
