@@ -496,209 +496,6 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// The same blocked apply, TMA-staged (L <= 104 trailing rows).  A basis tile's trailing rows are one
-// contiguous L KB burst in HBM: a persistent CTA brings them into shared memory with one 1 KB bulk
-// copy per row (rows land at a pitch of 130 doubles, which makes the DMMA fragment accesses -- 4
-// rows x 8 columns per warp instruction -- bank-conflict free), the 8 warps update 16 columns each in
-// place, and the rows below the block leave with one bulk store per row.  Two stages: the loads of
-// tile k+1 and the stores of tile k-1 are in flight while tile k is computed; no thread ever
-// executes a global load or store for the matrix.
-// ---------------------------------------------------------------------------------------------
-constexpr int AT_THREADS = 256;
-constexpr int AT_LD = OMB_TB + 2;          // 2 * AT_LD == 4 (mod 16): rows 2p, columns cq -> 16 distinct bank pairs
-constexpr int AT_STAGES = 2;
-constexpr int AT_LMAX = 104;
-
-static size_t apply_tma_smem(int L) { return sizeof(double) * (size_t)AT_STAGES * L * AT_LD; }
-
-template <int LG>
-__global__ void __launch_bounds__(AT_THREADS)
-qr_apply_tma_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L, int t,
-                    const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-                    int64_t s_total, Shard sh, Cand* __restrict__ cand)
-{
-    constexpr int LP = LG * 8;                 // padded rows
-    constexpr int SVT = LP + 2;                // row stride of sVt [refl][row]: == 2 (mod 8)
-    constexpr int NG = 2;                      // 16 columns per warp, 8 warps = one tile
-    extern __shared__ __align__(128) double stage[];          // [AT_STAGES][L][AT_LD]
-    __shared__ __align__(8) uint64_t full_bar[AT_STAGES];
-    __shared__ double sV[LP * AM_SV];
-    __shared__ double sVt[8 * SVT];
-    __shared__ double sT[8 * AM_ST];
-    __shared__ Cand s_c[AT_THREADS / 32];
-    for (int e = threadIdx.x; e < LP * 8; e += AT_THREADS) {
-        const int k = e >> 3, a = e & 7;
-        const double v = (k < L && a <= t) ? P->V[a][k] : 0.0;
-        sV[k * AM_SV + a] = v;
-        sVt[a * SVT + k] = v;
-    }
-    if (threadIdx.x < 64) {
-        const int a = threadIdx.x >> 3, b = threadIdx.x & 7;
-        sT[a * AM_ST + b] = (a <= b && b <= t) ? P->T[a][b] : 0.0;
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < AT_STAGES; ++s) mbar_init(&full_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p = lane & 3, cq = lane >> 2;
-    const int tG = t >> 3, tp = (t & 7) >> 1, te = t & 1;
-    const bool last_row = (t + 1 == L);
-    const int64_t ntiles = basis_tiles(n);
-    const size_t stage_doubles = (size_t)L * AT_LD;
-    const int64_t tile_stride = (int64_t)r * OMB_TB;
-
-    // warp 0 drives the copies: lane l moves rows l, l + 32, ...
-    auto issue_load = [&](int64_t tile, int s) {
-        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(L * OMB_TB * sizeof(double)));
-        __syncwarp();
-        const double* g = src + tile * tile_stride + (int64_t)i0 * OMB_TB;
-        double* d = stage + (size_t)s * stage_doubles;
-        for (int k = lane; k < L; k += 32) tma_load_bulk(d + k * AT_LD, g + (int64_t)k * OMB_TB, OMB_TB * sizeof(double), &full_bar[s]);
-    };
-    int64_t tile = blockIdx.x;
-    if (warp == 0 && tile < ntiles) issue_load(tile, 0);
-
-    Cand best = cand_empty();
-    int it = 0;
-    for (; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        const int64_t ntile = tile + gridDim.x;
-        if (warp == 0 && ntile < ntiles) {
-            tma_store_wait_read();             // the stores of tile it-1 (this lane's) have left stage s^1
-            issue_load(ntile, s ^ 1);
-        }
-        mbar_wait(&full_bar[s], (uint32_t)((it >> 1) & 1));
-        double* sC = stage + (size_t)s * stage_doubles + (2 * p) * AT_LD + warp * (8 * NG) + cq;
-        const int64_t j0 = tile * OMB_TB + warp * (8 * NG);
-        double pv1[NG], pv2[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int64_t j = j0 + 8 * g + cq;
-            const bool owner = (p == tp) && (j < n);
-            pv1[g] = owner ? vn1[j] : -1.0;
-            pv2[g] = owner ? vn2[j] : 1.0;
-        }
-        double c[LG][NG][2];
-#pragma unroll
-        for (int G = 0; G < LG; ++G)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int row = 8 * G + 2 * p + e;
-#pragma unroll
-                for (int g = 0; g < NG; ++g) c[G][g][e] = (row < L) ? sC[(8 * G + e) * AT_LD + 8 * g] : 0.0;
-            }
-        // Z^T = C^T V
-        double z[NG][2];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) z[g][0] = z[g][1] = 0.0;
-#pragma unroll
-        for (int G = 0; G < LG; ++G)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double bv = sV[(8 * G + 2 * p + e) * AM_SV + cq];
-#pragma unroll
-                for (int g = 0; g < NG; ++g) dmma884(z[g][0], z[g][1], c[G][g][e], bv);
-            }
-        // Z'^T = Z^T T
-        double zp[NG][2];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) zp[g][0] = zp[g][1] = 0.0;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const double bv = sT[(2 * p + e) * AM_ST + cq];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) dmma884(zp[g][0], zp[g][1], z[g][e], bv);
-        }
-        // C^T -= Z'^T V^T
-#pragma unroll
-        for (int g = 0; g < NG; ++g) { zp[g][0] = -zp[g][0]; zp[g][1] = -zp[g][1]; }
-#pragma unroll
-        for (int G = 0; G < LG; ++G)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double bv = sVt[(2 * p + e) * SVT + 8 * G + cq];
-#pragma unroll
-                for (int g = 0; g < NG; ++g) dmma884(c[G][g][0], c[G][g][1], zp[g][e], bv);
-            }
-        // rows below the block go back to the stage (in place: a warp owns its 16 columns); R[i, j] = row t
-        double rij[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) rij[g] = 0.0;
-#pragma unroll
-        for (int G = 0; G < LG; ++G)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int row = 8 * G + 2 * p + e;
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    if (G == tG && e == te) rij[g] = c[G][g][e];
-                    if (row > t && row < L) sC[(8 * G + e) * AT_LD + 8 * g] = c[G][g][e];
-                }
-            }
-        // down-date: the lanes holding row t (p == tp) own their column's norms
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int64_t j = j0 + 8 * g + cq;
-            const bool owner = (p == tp) && (j < n);
-            double v1 = pv1[g];
-            bool redo = false;
-            if (owner && v1 > 0.0) redo = downdate(rij[g], v1, pv2[g]);
-            if (__any_sync(0xFFFFFFFFu, redo)) {
-                // exact trailing norm: each of the column's 4 lanes sums its rows, then combine
-                double sq = 0.0;
-#pragma unroll
-                for (int G = 0; G < LG; ++G)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int row = 8 * G + 2 * p + e;
-                        if (row > t && row < L) sq = fma(c[G][g][e], c[G][g][e], sq);
-                    }
-                sq += __shfl_xor_sync(0xFFFFFFFFu, sq, 1);
-                sq += __shfl_xor_sync(0xFFFFFFFFu, sq, 2);
-                if (redo) {
-                    v1 = last_row ? 0.0 : sqrt(sq);
-                    vn2[j] = v1;
-                }
-            }
-            if (owner && v1 >= 0.0) {
-                vn1[j] = v1;
-                cand_push_lazy(best, v1, j, sh, P, s_total);
-            }
-        }
-        fence_proxy_async();                   // the updated rows become visible to the bulk stores
-        __syncthreads();
-        if (warp == 0) {
-            const double* sr = stage + (size_t)s * stage_doubles;
-            double* g = dst + tile * tile_stride + (int64_t)i0 * OMB_TB;
-            for (int k = t + 1 + lane; k < L; k += 32) tma_store_bulk(g + (int64_t)k * OMB_TB, sr + k * AT_LD, OMB_TB * sizeof(double));
-            tma_store_commit();
-        }
-    }
-    if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    best = cand_block_reduce(best, s_c);
-    if (threadIdx.x == 0) {
-        cand[blockIdx.x] = best;
-        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
-    }
-}
-
-typedef void (*ApplyTmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
-                           int64_t, Shard, Cand*);
-static ApplyTmaFn pick_apply_tma(int L)
-{
-    switch ((L + 7) / 8) {
-#define OMB_AT_CASE(LGV) case LGV: return qr_apply_tma_kernel<LGV>;
-        OMB_AT_CASE(1) OMB_AT_CASE(2) OMB_AT_CASE(3) OMB_AT_CASE(4) OMB_AT_CASE(5) OMB_AT_CASE(6) OMB_AT_CASE(7)
-        OMB_AT_CASE(8) OMB_AT_CASE(9) OMB_AT_CASE(10) OMB_AT_CASE(11) OMB_AT_CASE(12) OMB_AT_CASE(13)
-#undef OMB_AT_CASE
-        default: return nullptr;
-    }
-}
-
 typedef void (*ApplyMmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
                            int64_t, Shard, Cand*);
 
@@ -1122,13 +919,6 @@ static int qr_start(const double* d_Ut, int64_t n, int r, int64_t s, const doubl
     return 0;
 }
 
-static bool apply_tma_enabled()
-{
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("OMB_QR_APPLY"); on = (e && e[0] == 't') ? 1 : 0; }   // OMB_QR_APPLY=tma: opt in
-    return on == 1;
-}
-
 // the pass that follows the panel of step i (block-local step t of the block starting at i0)
 static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t s, int block, int i0, int t,
                    const QrWs& w, Shard sh, cudaStream_t st, int* ncand)
@@ -1150,19 +940,6 @@ static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t 
         } else {
             // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
             //  tensor-path rounding instead of the oracle's fma order)
-            ApplyTmaFn ft = (L <= AT_LMAX && apply_tma_enabled()) ? pick_apply_tma(L) : nullptr;
-            if (ft) {
-                const size_t smem = apply_tma_smem(L);
-                int per_sm = (int)((size_t)220 * 1024 / (smem + 4096));
-                per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
-                g = ntiles < (int64_t)sms * per_sm ? ntiles : (int64_t)sms * per_sm;
-                if (g > QR_NCAND) g = QR_NCAND;
-                OMB_CUDA(cudaFuncSetAttribute(ft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ft<<<(unsigned)g, AT_THREADS, smem, st>>>(src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand);
-                if ((rc = check_launch("qr_apply_tma_kernel"))) return rc;
-                *ncand = (int)g;
-                return 0;
-            }
             ApplyMmaFn fm = pick_apply_mma(L, &ng);
             g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
             if (g > (int64_t)sms * 3) g = (int64_t)sms * 3;
