@@ -347,56 +347,53 @@ gram_small_kernel(const double* __restrict__ X, int64_t n_c, int m, const double
         for (int a = 0; a < NB; ++a)
 #pragma unroll
             for (int b = 0; b < NB; ++b) c[a][b][0] = c[a][b][1] = 0.0;
-        bool colok[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) colok[b] = (8 * b + fc) < m;
-
         const int rowc = 4 * warp + fr;                             // this lane's row inside every chunk
-        const int noct = m >> 3, rem = m & 7;
+        const int rem = m & 7;                                      // rem != 0: block NB-1 is the ragged octet
+        const bool has_tail = rem != 0;
+        const bool lastcol_ok = (8 * (NB - 1) + fc) < m;
         const double dm = (double)m;
         const int64_t myrow0 = row_lo + rowc;
         double* cnt_dst = cnt_out ? cnt_out + (int64_t)f * n_c + myrow0 : nullptr;
+        const double* px0 = smem + rowc * m + fc;
         for (int ch = 0; ch < nchunks; ++ch) {
             const int s = ch % GS_STAGES;
             mbar_wait(&full_bar[s], (ch / GS_STAGES) & 1);
-            const double* sX = smem + s * stage_doubles;
-            const double* sC = sX + ((GS_CH * m + 1) & ~1);
-            const bool rok = (myrow0 + (int64_t)ch * GS_CH) < row_hi;
             // unconditional loads (columns >= m read the next row / the slack behind the ring: always
             // inside shared memory), masked afterwards: no branches in the chunk loop
-            const double* px = sX + rowc * m + fc;
+            const double* px = px0 + s * stage_doubles;
             double a[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) a[b] = px[8 * b];
-            double cv = cf ? sC[rowc] : 0.0;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? a[b] : 0.0;
+            double cv = cf ? smem[s * stage_doubles + ((GS_CH * m + 1) & ~1) + rowc] : 0.0;
             if (cnt_out) {
                 // np.average(x, axis=1) from the fragments already in registers: lane fc of a row's
                 // 8 lanes holds numpy's accumulator fc (a[0] + a[1] + ... over the full octets), the
                 // shuffles are numpy's ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the m % 8 tail.
-                double sacc = -0.0, tail = 0.0;
+                double sacc;
+                if (NB == 1) {
+                    sacc = has_tail ? -0.0 : a[0];
+                } else {
+                    sacc = a[0];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (b == 0) sacc = noct > 0 ? a[0] : sacc;
-                    else sacc = b < noct ? sacc + a[b] : sacc;
-                    tail = b == noct ? a[b] : tail;
+                    for (int b = 1; b < NB - 1; ++b) sacc += a[b];
+                    if (!has_tail) sacc += a[NB - 1];
                 }
-                if (noct > 0) {
+                if (!(NB == 1 && has_tail)) {
                     sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 4);
                     sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 8);
                     sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, 16);
                 }
-#pragma unroll
-                for (int e = 0; e < 7; ++e) {
-                    const double tv = __shfl_sync(0xFFFFFFFFu, tail, fr + 4 * e);
-                    sacc = e < rem ? sacc + tv : sacc;
-                }
+                for (int e = 0; e < rem; ++e) sacc += __shfl_sync(0xFFFFFFFFu, a[NB - 1], fr + 4 * e);
                 cv = sacc / dm;
-                if (fc == 0 && rok) cnt_dst[(int64_t)ch * GS_CH] = cv;
+                if (fc == 0 && myrow0 + (int64_t)ch * GS_CH < row_hi) cnt_dst[(int64_t)ch * GS_CH] = cv;
             }
 #pragma unroll
-            for (int b = 0; b < NB; ++b) a[b] = (rok && colok[b]) ? a[b] - cv : 0.0;
+            for (int b = 0; b < NB - 1; ++b) a[b] -= cv;
+            a[NB - 1] = lastcol_ok ? a[NB - 1] - cv : 0.0;
+            if (ch == nchunks - 1 && !(myrow0 + (int64_t)ch * GS_CH < row_hi)) {      // rows past the split's end
+#pragma unroll
+                for (int b = 0; b < NB; ++b) a[b] = 0.0;
+            }
             __syncwarp();                                          // every lane holds its (used) values
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
 #pragma unroll

@@ -942,7 +942,9 @@ static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t 
             //  tensor-path rounding instead of the oracle's fma order)
             ApplyMmaFn fm = pick_apply_mma(L, &ng);
             g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
-            if (g > (int64_t)sms * 3) g = (int64_t)sms * 3;
+            int per_sm = 0;                    // resident CTAs per SM of this instantiation: one full wave
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fm, AM_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+            if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
             if (g > QR_NCAND) g = QR_NCAND;
             fm<<<(unsigned)g, AM_THREADS, 0, st>>>(src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand);
             if ((rc = check_launch("qr_apply_mma_kernel"))) return rc;
