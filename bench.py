@@ -415,7 +415,8 @@ def main():
             "config": {"workload": w["name"], "rows_per_gpu": n_loc, "rows": n_glob, "snapshots": m, "modes": r,
                        "sensors": r, "scale_type": w["scale_type"], "qr_block": QR_BLOCK,
                        "l2": "inputs (%.0f MB per GPU) exceed the 126 MB L2" % (8.0 * n_loc * m / 1e6),
-                       "parallelism": "cells sharded over %d rank(s)" % world},
+                       "parallelism": "cells sharded over %d rank(s)" % world,
+                       "qr_exchange": getattr(spr._eng, "qr_exchange", "none (single rank)")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms": stages, "step_ms": [round(v, 3) for v in step_ms], "reconstruct": recon,
             "pivots_head": [int(p) for p in spr.qr_pivots[:8]], "min_pivot_gap": float(spr.qr_gap.min()),
