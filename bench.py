@@ -252,9 +252,11 @@ def main():
     clocks = Clocks(local_rank) if rank == 0 and not os.environ.get("OMB_BENCH_NO_CLOCKS") else None
     if clocks:
         clocks.start()
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(max(args.warmup, 3)):          # identical to the timed steps (events included)
+        step(timed_qr=True)
+        torch.cuda.Event(enable_timing=True).record()
     sync_all()
+    qr_events.clear()
     L.omb_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
