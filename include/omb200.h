@@ -147,6 +147,7 @@ int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, int64_t r, i
  * call and identical on every rank.  After synchronising, a non-zero int64 at
  * d_mine + 2*world*record_doubles + 3*world means a peer never answered (10 s timeout). */
 int64_t omb_qrcp_p2p_buffer_doubles(int world);
+int64_t omb_qrcp_p2p_error_index(int world);   /* double index of the buffer's time-out flag */
 int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
                  void* d_ws, int block, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world,
                  const void* d_peers, double* d_mine, int64_t epoch, int64_t* d_piv, double* d_rdiag,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "omb_qrcp_mr_local": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "omb_qrcp_mr_step": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _i64, _i64, _i64, _i64, _int, _int, _vp,
                                  _vp, _vp, _vp, _vp]),
+    "omb_qrcp_p2p_error_index": (_i64, [_int]),
     "omb_qrcp_p2p_buffer_doubles": (_i64, [_int]),
     "omb_qrcp_p2p": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _i64, _i64, _int, _int, _vp, _vp,
                              _i64, _vp, _vp, _vp, _vp]),

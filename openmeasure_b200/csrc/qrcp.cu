@@ -535,22 +535,66 @@ __device__ __forceinline__ double block_sum(double x, double* s_red)
 }
 
 // ---- peer-to-peer exchange over NVLink (symmetric memory): every rank owns a buffer laid out as
-//   recs [2][world][QR_REC] doubles | step flags [2][world] int64 | barrier flags [world] int64 | error int64
-// and holds the device addresses of all ranks' buffers.  A record is published by storing it into
-// slot [parity][my_rank] of EVERY peer's buffer, fencing, and then storing the step flag; the
-// consumer spins on its OWN copy of the flags.  Flag values only grow (epoch * 4096 + step + 1).
+//   LL slots [2 parity][world][2 * QR_REC] u64 | (reserved [2][world]) | barrier flags [world] i64 | error i64
+// and holds the device addresses of all ranks' buffers.  A record travels in the low-latency format
+// of the collective libraries: every 8-byte word carries 4 bytes of payload and a 4-byte step tag,
+// so the receiver needs neither a fence nor a separate flag -- a word whose tag matches IS the data
+// (8-byte stores are single NVLink transactions).  The sender stores the 2 * (8 + L) words of its
+// record into slot [step parity][its rank] of EVERY peer's buffer; the receiver polls its OWN copy.
+// Tags only grow (epoch * 4096 + step + 1), the buffer starts zeroed.
 struct P2P {
     double* const* peers;     // device array of `world` buffer addresses (NULL: host-gathered path)
     double* mine;             // this rank's buffer
     int64_t epoch;
 };
-__device__ __forceinline__ double* p2p_rec(double* buf, int world, int parity, int src)
+__device__ __forceinline__ unsigned long long* p2p_ll(double* buf, int world, int parity, int src)
 {
-    return buf + ((int64_t)parity * world + src) * QR_REC;
+    return reinterpret_cast<unsigned long long*>(buf) + ((int64_t)parity * world + src) * (2 * QR_REC);
 }
 __device__ __forceinline__ int64_t* p2p_flags(double* buf, int world)
 {
-    return reinterpret_cast<int64_t*>(buf + (int64_t)2 * world * QR_REC);
+    return reinterpret_cast<int64_t*>(buf + (int64_t)4 * world * QR_REC);
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// publish word k of a record to every peer (payload d, tag)
+__device__ __forceinline__ void ll_publish(const P2P& pp, int world, int parity, int rank, int k, double d, unsigned tag)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    const unsigned long long w0 = (bits & 0xFFFFFFFFull) | ((unsigned long long)tag << 32);
+    const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+    for (int g = 0; g < world; ++g) {
+        unsigned long long* dst = p2p_ll(pp.peers[g], world, parity, rank) + 2 * k;
+        st_relaxed_sys(dst, w0);
+        st_relaxed_sys(dst + 1, w1);
+    }
+}
+// wait for word k of rank src's record in MY buffer; gives up after ~10 s and raises the error word
+__device__ __forceinline__ double ll_receive(const P2P& pp, int world, int parity, int src, int k, unsigned tag, int64_t* err)
+{
+    const unsigned long long* p = p2p_ll(pp.mine, world, parity, src) + 2 * k;
+    unsigned long long w0, w1, t0 = 0;
+    unsigned spins = 0;
+    for (;;) {
+        w0 = ld_relaxed_sys(p);
+        w1 = ld_relaxed_sys(p + 1);
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if ((++spins & 0x3FFu) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 10000000000ull) { *err = 1; break; }
+        }
+    }
+    return __longlong_as_double((long long)((w0 & 0xFFFFFFFFull) | (w1 << 32)));
 }
 __device__ __forceinline__ void st_release_sys(int64_t* p, int64_t v)
 {
@@ -590,8 +634,8 @@ __global__ void qr_p2p_barrier_kernel(P2P pp, int rank, int world)
     if (g < world) p2p_wait(myflags + 2 * world + g, pp.epoch, myflags + 3 * world);
 }
 
-// multi-rank step A (1 CTA): local argmax + the winner's trailing column -> one record, written to
-// `rec` (host-gathered path) or published to every peer (P2P path)
+// multi-rank step A of the host-gathered path (1 CTA): local argmax + the winner's trailing column ->
+// one record in `rec` (the P2P path does this inside the panel kernel)
 __global__ void __launch_bounds__(PN_THREADS)
 qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, const double* __restrict__ src, int r,
                 int i0, int L, int step, Shard sh, double* __restrict__ rec, P2P pp)
@@ -617,21 +661,8 @@ qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, cons
     for (int k = threadIdx.x; k < L; k += PN_THREADS)
         s_rec[8 + k] = (p >= 0) ? src[basis_index(i0 + k, p, r)] : 0.0;
     __syncthreads();
-    if (pp.peers == nullptr) {
-        for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) rec[k] = s_rec[k];
-        return;
-    }
-    const int parity = step & 1;
-    for (int g = 0; g < sh.world; ++g) {
-        double* dst = p2p_rec(pp.peers[g], sh.world, parity, sh.rank);
-        for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) dst[k] = s_rec[k];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < sh.world) {
-        int64_t* peer_flags = p2p_flags(pp.peers[threadIdx.x], sh.world);
-        st_release_sys(peer_flags + parity * sh.world + sh.rank, pp.epoch * 4096 + step + 1);
-    }
+    (void)step; (void)pp;
+    for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) rec[k] = s_rec[k];
 }
 
 // The panel is pure latency (one CTA between two grid-wide passes), so it is organised around
@@ -664,15 +695,17 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
 
     Cand c = cand_empty();       // winner: idx = GLOBAL row index, key = LAPACK position
     int64_t p_local = -1;        // the winner's local column, -1 if another rank owns it
-    if (!MULTI) {
-        // 1. global argmax over the pass kernel's records: all loads first, then the merges
+    const bool p2p = MULTI && pp.peers != nullptr;
+    if (!MULTI || p2p) {
+        // 1. argmax over this rank's pass-kernel records: all loads first, then the merges
         constexpr int NR = 5;
+        const int nc = MULTI ? P->ncand : ncand;
         Cand rc[NR];
 #pragma unroll
         for (int u = 0; u < NR; ++u) {
             const int e = threadIdx.x + u * PN_THREADS;
             rc[u] = cand_empty();
-            if (e < ncand) {
+            if (e < nc) {
                 const double2 lo = *reinterpret_cast<const double2*>(&cand[e].best);
                 const longlong2 hi = *reinterpret_cast<const longlong2*>(&cand[e].idx);
                 rc[u].best = lo.x; rc[u].second = lo.y; rc[u].idx = hi.x; rc[u].key = hi.y;
@@ -680,7 +713,7 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         }
 #pragma unroll
         for (int u = 0; u < NR; ++u) cand_merge(c, rc[u]);
-        for (int e = threadIdx.x + NR * PN_THREADS; e < ncand; e += PN_THREADS) cand_merge(c, cand[e]);
+        for (int e = threadIdx.x + NR * PN_THREADS; e < nc; e += PN_THREADS) cand_merge(c, cand[e]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { Cand b = cand_shfl_xor(c, o); cand_merge(c, b); }
         if (lane == 0) s_c[warp] = c;
@@ -692,18 +725,47 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         c.idx = __shfl_sync(0xFFFFFFFFu, c.idx, 0); c.key = __shfl_sync(0xFFFFFFFFu, c.key, 0);
         p_local = c.idx;
         // 2. pivot column tail at block start (every warp knows the winner: no second barrier)
-        const double* col = src + basis_index(i0, p_local, r);
-        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = col[(int64_t)k * OMB_TB];
-    } else {
-        if (pp.peers != nullptr) {
-            // P2P path: wait until every rank's record of this step has landed in MY buffer
-            int64_t* myflags = p2p_flags(pp.mine, sh.world);
-            if (threadIdx.x < sh.world)
-                p2p_wait(myflags + (i & 1) * sh.world + threadIdx.x, pp.epoch * 4096 + i + 1, myflags + 3 * sh.world);
-            __syncthreads();
-            recs = p2p_rec(pp.mine, sh.world, i & 1, 0);
+        const double* col = src + basis_index(i0, p_local < 0 ? 0 : p_local, r);
+        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = p_local >= 0 ? col[(int64_t)k * OMB_TB] : 0.0;
+    }
+    if (p2p) {
+        // 3. exchange over NVLink: publish (header, column tail) to every peer in the tagged low-latency
+        //    format, collect the world's headers, pick the winner in rank order (identical decision on
+        //    every rank), then collect the winner's column tail
+        __shared__ double s_hdr[64][8];
+        const unsigned tag = (unsigned)(pp.epoch * 4096 + i + 1);
+        const int parity = i & 1;
+        int64_t* err = p2p_flags(pp.mine, sh.world) + 3 * sh.world;
+        __syncthreads();                     // s_x complete
+        for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) {
+            double d = 0.0;
+            if (k == 0) d = c.best;
+            else if (k == 1) d = c.second;
+            else if (k == 2) d = __longlong_as_double(c.key);
+            else if (k == 3) d = __longlong_as_double(c.idx >= 0 ? glob_index(c.idx, sh) : -1);
+            else if (k == 4) d = __longlong_as_double(c.idx);
+            else if (k >= 8) d = s_x[k - 8];
+            ll_publish(pp, sh.world, parity, sh.rank, k, d, tag);
         }
-        // 1. winner among the ranks' records (fixed order: identical decision on every rank)
+        for (int e = threadIdx.x; e < sh.world * 8; e += PN_THREADS)
+            s_hdr[e >> 3][e & 7] = ll_receive(pp, sh.world, parity, e >> 3, e & 7, tag, err);
+        __syncthreads();
+        c = cand_empty();
+        p_local = -1;
+        int wr = -1;
+        for (int g = 0; g < sh.world; ++g) {
+            Cand b;
+            b.best = s_hdr[g][0]; b.second = s_hdr[g][1];
+            b.key = __double_as_longlong(s_hdr[g][2]); b.idx = __double_as_longlong(s_hdr[g][3]);
+            if (b.idx < 0) continue;
+            const bool wins = cand_better(b.best, b.key, c.best, c.key);
+            cand_merge(c, b);
+            if (wins) { wr = g; p_local = (g == sh.rank) ? __double_as_longlong(s_hdr[g][4]) : -1; }
+        }
+        if (wr < 0) wr = 0;
+        for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = ll_receive(pp, sh.world, parity, wr, 8 + k, tag, err);
+    } else if (MULTI) {
+        // host-gathered records: winner among the ranks in fixed order
         int wr = -1;
         for (int g = 0; g < sh.world; ++g) {
             const double* rcp = recs + (int64_t)g * QR_REC;
@@ -1071,7 +1133,9 @@ extern "C" int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, i
 // peer memory (no NCCL call, no host round trip inside the loop).  d_peers: device array of `world`
 // symmetric-buffer addresses (entry `rank` == d_mine), each omb_qrcp_p2p_buffer_doubles(world) doubles,
 // zero-filled once at allocation.  epoch: strictly increasing per call, identical on every rank.
-extern "C" int64_t omb_qrcp_p2p_buffer_doubles(int world) { return (int64_t)2 * world * QR_REC + 3 * world + 8; }
+extern "C" int64_t omb_qrcp_p2p_buffer_doubles(int world) { return (int64_t)4 * world * QR_REC + 3 * world + 8; }
+// index (in doubles) of the buffer's error word: non-zero after a peer failed to answer within 10 s
+extern "C" int64_t omb_qrcp_p2p_error_index(int world) { return (int64_t)4 * world * QR_REC + 3 * world; }
 
 extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
                             void* d_ws, int block, int64_t n_c_loc, int64_t n_c, int64_t cell0, int rank, int world,
@@ -1096,8 +1160,6 @@ extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s,
     int i0 = 0;
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        qr_local_kernel<<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, src, ri, i0, ri - i0, i, sh, nullptr, pp);
-        if ((rc = check_launch("qr_local_kernel"))) return rc;
         qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, i, t, 0, s, 0, sh,
                                                          nullptr, pp, w.vn1, d_piv, d_rdiag, d_gap);
         if ((rc = check_launch("qr_panel_kernel"))) return rc;

@@ -257,7 +257,7 @@ class Engine:
             _lib.call("omb_qrcp_p2p", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(work), _p(ws), block,
                       *self._shard_args(), C.c_void_p(p2p["peers_dev"]), _p(p2p["buf"]), p2p["epoch"],
                       _p(piv), _p(rdiag), _p(gap), _stream())
-            self._p2p_err = (p2p["buf"], 2 * self.world * int(L.omb_qrcp_record_doubles()) + 3 * self.world)
+            self._p2p_err = (p2p["buf"], int(L.omb_qrcp_p2p_error_index(self.world)))
             return piv, rdiag, gap
         nrec = int(L.omb_qrcp_record_doubles())
         rec = torch.zeros(nrec, dtype=torch.float64, device=self.dev)
