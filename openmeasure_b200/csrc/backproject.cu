@@ -96,12 +96,12 @@ backproject_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, 
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const int i = ib + a * 8 + fc;
-                const double sv = s_scl[i];
+                const double isv = 1.0 / s_scl[i];
 #pragma unroll
                 for (int b = 0; b < QB; ++b) {
                     const int q = b * 8 + 2 * fr;
-                    sC[q * BP_LDC + i] = c[a][b][0] / sv;
-                    sC[(q + 1) * BP_LDC + i] = c[a][b][1] / sv;
+                    sC[q * BP_LDC + i] = c[a][b][0] * isv;
+                    sC[(q + 1) * BP_LDC + i] = c[a][b][1] * isv;
                 }
             }
             __syncthreads();
@@ -230,16 +230,19 @@ backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, i
         // the previous tile's bulk store must have finished reading sC before it is overwritten
         if (threadIdx.x == 0) tma_store_wait_read();
         __syncthreads();
+        // 1/scl once per row: an FP64 division is a ~12-instruction sequence with a slow-path branch, and
+        // 4 QB of them per lane were 85 % of this kernel's stall samples
+        const double is0 = 1.0 / cur.s0, is1 = 1.0 / cur.s1;
 #pragma unroll
         for (int b = 0; b < QB; ++b) {
             const int q = b * 8 + 2 * fr;
             if (q < r) {
-                sC[q * OMB_TB + warp * 16 + fc] = acc[0][b][0] / cur.s0;
-                sC[q * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][0] / cur.s1;
+                sC[q * OMB_TB + warp * 16 + fc] = acc[0][b][0] * is0;
+                sC[q * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][0] * is1;
             }
             if (q + 1 < r) {
-                sC[(q + 1) * OMB_TB + warp * 16 + fc] = acc[0][b][1] / cur.s0;
-                sC[(q + 1) * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][1] / cur.s1;
+                sC[(q + 1) * OMB_TB + warp * 16 + fc] = acc[0][b][1] * is0;
+                sC[(q + 1) * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][1] * is1;
             }
         }
         fence_proxy_async();
@@ -407,11 +410,12 @@ backproject_big_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int i = ib + 8 * p + fc;
+            const double isv = 1.0 / sv[p];                    // one division per row, not per element
             double ss = 0.0;
 #pragma unroll
             for (int q = 0; q < QH; ++q) {
                 const int col = jb + 8 * q + 2 * fr;           // mode index inside this launch
-                const double u0 = acc[p][q][0] / sv[p], u1 = acc[p][q][1] / sv[p];
+                const double u0 = acc[p][q][0] * isv, u1 = acc[p][q][1] * isv;
                 if (col < qv) { if (rok[p]) stg_stream(tbase + (int64_t)(q0 + col) * OMB_TB + i, u0); ss = fma(u0, u0, ss); }
                 if (col + 1 < qv) { if (rok[p]) stg_stream(tbase + (int64_t)(q0 + col + 1) * OMB_TB + i, u1); ss = fma(u1, u1, ss); }
             }
