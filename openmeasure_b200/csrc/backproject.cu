@@ -141,9 +141,8 @@ static int launch_bp(const double* X, int64_t n, int64_t n_c, int m, const doubl
 // The A fragments (X - cnt, 8 rows x 4 snapshots = eight 32-byte sectors per load) are read
 // straight from global memory -- a row's 8m bytes stay in L1 across its ceil(m/4) k-steps -- so X
 // makes exactly one trip from HBM and there is no shared-memory staging or barrier in the main
-// loop.  W is staged once per CTA.  The 128 x r result tile is assembled in shared memory in the
-// tile's own layout [q][128] and leaves with ONE bulk (TMA) store of r KB; the dgeqp3 norms are
-// summed from the same tile, sequentially over the modes.
+// loop.  W is staged once per CTA.  The result leaves straight from the accumulator fragments (64-byte
+// runs of the tile layout) and the dgeqp3 norms are reduced by shuffles: no barrier per tile.
 // ---------------------------------------------------------------------------------------------
 constexpr int BS_THREADS2 = 256;
 
@@ -156,8 +155,7 @@ backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, i
     constexpr int QC = QB * 8;
     constexpr int LDW = QC + 4;                    // == 4 (mod 16)
     extern __shared__ __align__(128) double smem[];
-    double* sC = smem;                             // [r][128]   (tile layout, bulk-stored)
-    double* sW = smem + 64 * OMB_TB;               // [mp][LDW]
+    double* sW = smem;                             // [mp][LDW]
     const int mp = (m + 3) & ~3;
     for (int e = threadIdx.x; e < mp * QC; e += BS_THREADS2) {
         const int k = e / QC, q = e - k * QC;
@@ -227,39 +225,40 @@ backproject_small_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, i
 #pragma unroll
             for (int u = 0; u < KU; ++u) { v0[u] = w0[u]; v1[u] = w1[u]; }
         }
-        // the previous tile's bulk store must have finished reading sC before it is overwritten
-        if (threadIdx.x == 0) tma_store_wait_read();
-        __syncthreads();
-        // 1/scl once per row: an FP64 division is a ~12-instruction sequence with a slow-path branch, and
-        // 4 QB of them per lane were 85 % of this kernel's stall samples
-        const double is0 = 1.0 / cur.s0, is1 = 1.0 / cur.s1;
+        // epilogue without staging or barriers: an accumulator fragment is eight consecutive candidates
+        // of one mode = one 64-byte run of the tile; the warps never meet, so the epilogue of one warp
+        // overlaps the DMMAs of the others (a staged tile + one bulk store cost two CTA barriers and a
+        // 40-step norm loop per tile: the tensor pipe idled half of the time)
+        {
+            const double is0 = 1.0 / cur.s0, is1 = 1.0 / cur.s1;      // one reciprocal per row
+            double* tb = Ut + tile * ((int64_t)r * OMB_TB) + warp * 16 + fc;
+            double ss0 = 0.0, ss1 = 0.0;
 #pragma unroll
-        for (int b = 0; b < QB; ++b) {
-            const int q = b * 8 + 2 * fr;
-            if (q < r) {
-                sC[q * OMB_TB + warp * 16 + fc] = acc[0][b][0] * is0;
-                sC[q * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][0] * is1;
+            for (int b = 0; b < QB; ++b) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int q = b * 8 + 2 * fr + e;
+                    if (q < r) {
+                        const double u0 = acc[0][b][e] * is0, u1 = acc[1][b][e] * is1;
+                        if (cur.ok0) stg_stream(tb + (int64_t)q * OMB_TB, u0);
+                        if (cur.ok1) stg_stream(tb + (int64_t)q * OMB_TB + 8, u1);
+                        ss0 = fma(u0, u0, ss0);
+                        ss1 = fma(u1, u1, ss1);
+                    }
+                }
             }
-            if (q + 1 < r) {
-                sC[(q + 1) * OMB_TB + warp * 16 + fc] = acc[0][b][1] * is0;
-                sC[(q + 1) * OMB_TB + warp * 16 + 8 + fc] = acc[1][b][1] * is1;
+            if (vn) {
+                ss0 += __shfl_xor_sync(0xFFFFFFFFu, ss0, 1); ss0 += __shfl_xor_sync(0xFFFFFFFFu, ss0, 2);
+                ss1 += __shfl_xor_sync(0xFFFFFFFFu, ss1, 1); ss1 += __shfl_xor_sync(0xFFFFFFFFu, ss1, 2);
+                if (fr == 0) {
+                    if (cur.ok0) vn[tile * OMB_TB + warp * 16 + fc] = sqrt(ss0);
+                    if (cur.ok1) vn[tile * OMB_TB + warp * 16 + 8 + fc] = sqrt(ss1);
+                }
             }
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tma_store_bulk(Ut + tile * ((int64_t)r * OMB_TB), sC, (uint32_t)(r * OMB_TB * sizeof(double)));
-            tma_store_commit();
-        }
-        if (vn && threadIdx.x < OMB_TB) {
-            double nrm = 0.0;
-            for (int q = 0; q < r; ++q) { const double u = sC[q * OMB_TB + threadIdx.x]; nrm = fma(u, u, nrm); }
-            vn[tile * OMB_TB + threadIdx.x] = sqrt(nrm);
         }
         cur = nxt;
         tile = ntile;
     }
-    if (threadIdx.x == 0) tma_store_wait_read();
 }
 
 template <int QB>
@@ -267,7 +266,7 @@ static int launch_bp_small(const double* X, int64_t n, int64_t n_c, int m, const
                            const double* W, int r, double* Ut, double* vn, cudaStream_t st)
 {
     const int mp = (m + 3) & ~3;
-    const size_t bytes = sizeof(double) * (64 * OMB_TB + (size_t)mp * (QB * 8 + 4));
+    const size_t bytes = sizeof(double) * ((size_t)mp * (QB * 8 + 4));
     OMB_CUDA(cudaFuncSetAttribute(backproject_small_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     int64_t grid = basis_tiles(n);
     int64_t cap = (int64_t)sm_count() * 2;
