@@ -280,7 +280,7 @@ static bool gram_big_ok(const double* X, int64_t m)
 // Warps are combined in a fixed order through shared memory; the CTA's partial goes out in the
 // 64 x 64 tile format of the general kernel and is reduced by the same fixed-order pass.
 // ---------------------------------------------------------------------------------------------
-constexpr int GS_WARPS = 12;                      // consumer warps: warp w owns k-step w of every chunk
+constexpr int GS_WARPS = 15;                      // consumer warps: warp w owns k-step w of every chunk
 constexpr int GS_THREADS = (GS_WARPS + 1) * 32;   // + one producer warp driving the TMA ring
 constexpr int GS_CH = 4 * GS_WARPS;               // rows per chunk
 constexpr int GS_STAGES = 4;
