@@ -3,7 +3,7 @@
 // Replaces the bidiagonal divide-and-conquer on R inside LAPACK dgesdd (np.linalg.svd, reference
 // sparse_sensing.py:272).  One CTA, matrix and eigenvectors in shared memory, cyclic two-sided
 // Jacobi with the round-robin parallel ordering (M/2 disjoint rotations per step, M-1 steps per
-// sweep).  A library syevd spends ~0.9 ms on an m = 41 Gram, mostly in
+// sweep), the tournament realised as a physical seat permutation.  A library syevd spends ~0.9 ms on an m = 41 Gram, mostly in
 // host synchronisation; Jacobi also resolves the small eigenvalues of a positive semi-definite
 // matrix to high relative accuracy.  Output: eigenvalues in DESCENDING order, V[i][k] = component
 // i of eigenvector k.
@@ -13,7 +13,7 @@
 namespace omb {
 
 constexpr int EJ_MAX = 64;
-constexpr int EJ_LD = EJ_MAX + 1;
+constexpr int EJ_LD = EJ_MAX + 2;            // even: rows stay 16-byte aligned for the 128-bit block loads
 constexpr int EJ_THREADS = 1024;
 constexpr int EJ_MAX_SWEEPS = 30;
 
@@ -54,16 +54,39 @@ __device__ __forceinline__ void jacobi_rot(double apq, double app, double aqq, d
     big = rel2 > 1.0e-18 * den && fabs(apq) > big_abs;
 }
 
-// the 2 x 2 block (rows p_i, q_i) x (columns p_j, q_j) of  J^T A J  for the rotations (ci, si), (cj, sj)
-struct Blk { double b00, b01, b10, b11; };
-__device__ __forceinline__ Blk jacobi_block(const double* __restrict__ A, int pi, int qi, int pj, int qj, double ci,
-                                            double si, double cj, double sj)
+// Round-robin tournament as a PHYSICAL permutation: pair k always sits at positions (2k, 2k+1) of the
+// rows/columns of A and the columns of V, and after every step the players move one seat (t_0 fixed,
+// t_k -> t_{k+1}, t_{n-1} -> b_{n-1}, b_k -> b_{k-1}, b_0 -> t_1; t_k = 2k, b_k = 2k+1).  The seat map
+// is the same every step, so a thread's source block (two 128-bit loads, consecutive threads =
+// consecutive columns: no bank conflicts) and its four destination entries are fixed for the whole
+// kernel: no schedule tables, no index arithmetic, no scattered gathers inside the sweeps.
+__device__ __forceinline__ int seat_next(int x, int n)
 {
-    const double a00 = A[pi * EJ_LD + pj], a01 = A[pi * EJ_LD + qj];
-    const double a10 = A[qi * EJ_LD + pj], a11 = A[qi * EJ_LD + qj];
+    if (n == 1 || x == 0) return x;
+    if (x == 1) return 2;
+    if (x & 1) return x - 2;
+    if (x == 2 * n - 2) return 2 * n - 1;
+    return x + 2;
+}
+__device__ __forceinline__ int seat_prev(int y, int n)
+{
+    if (n == 1 || y == 0) return y;
+    if (y == 2) return 1;
+    if (!(y & 1)) return y - 2;
+    if (y == 2 * n - 1) return 2 * n - 2;
+    return y + 2;
+}
+
+// the 2 x 2 block (pair i rows) x (pair j columns) of  J^T A J
+struct Blk { double b00, b01, b10, b11; };
+__device__ __forceinline__ Blk jacobi_block(const double* __restrict__ A, int i, int j, double2 ri, double2 rj)
+{
+    const double2 u0 = *reinterpret_cast<const double2*>(A + (2 * i) * EJ_LD + 2 * j);
+    const double2 u1 = *reinterpret_cast<const double2*>(A + (2 * i + 1) * EJ_LD + 2 * j);
+    const double ci = ri.x, si = ri.y, cj = rj.x, sj = rj.y;
     // columns (J_j), then rows (J_i^T)
-    const double b00 = cj * a00 - sj * a01, b01 = sj * a00 + cj * a01;
-    const double b10 = cj * a10 - sj * a11, b11 = sj * a10 + cj * a11;
+    const double b00 = cj * u0.x - sj * u0.y, b01 = sj * u0.x + cj * u0.y;
+    const double b10 = cj * u1.x - sj * u1.y, b11 = sj * u1.x + cj * u1.y;
     Blk o;
     o.b00 = ci * b00 - si * b10; o.b01 = ci * b01 - si * b11;
     o.b10 = si * b00 + ci * b10; o.b11 = si * b01 + ci * b11;
@@ -71,27 +94,29 @@ __device__ __forceinline__ Blk jacobi_block(const double* __restrict__ A, int pi
 }
 
 // ONE barrier per step.  While every thread applies the step's rotations to its fixed work items
-//   e <  npair^2 : block (pair i rows) x (pair j columns) of  A <- J^T A J   (A is ping-ponged between
-//                  two shared-memory copies: the blocks of a step tile the whole matrix)
-//   e >= npair^2 : two rows of  V <- V J  for one pair                       (single owner: in place)
-// npair look-ahead threads (the last ones of the CTA, idle otherwise) each re-derive the three entries
-// a_pq, a_pp, a_qq their pair of the NEXT step will see -- the same expressions, hence the same bits,
-// as the owners of those blocks compute -- and from them the next rotation.  The rotation chain
-// (~1000 cycles of dependent arithmetic) thereby runs beside the update instead of after it.
+//   e <  npair^2 : block (pair i) x (pair j) of  A <- J^T A J, written to its next seats
+//   e >= npair^2 : two rows of  V <- V J  for one pair, written to the pair's next column seats
+// (A and V are ping-ponged: a step rewrites both completely), npair look-ahead threads -- the last
+// ones of the CTA, idle otherwise -- each re-derive the three entries a_pp, a_pq, a_qq that the pair
+// of the NEXT step will find at its seats (the same expressions, hence the same bits, as the owners
+// of those blocks compute) and from them the next rotation.  The rotation chain (~1000 cycles of
+// dependent arithmetic) thereby runs beside the update instead of after it.
 __global__ void __launch_bounds__(EJ_THREADS)
 eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_out, double* __restrict__ V_out,
                    int* __restrict__ info)
 {
-    extern __shared__ double sm[];
-    double* A0 = sm;                          // [EJ_MAX][EJ_LD]
-    double* A1 = sm + EJ_MAX * EJ_LD;         // [EJ_MAX][EJ_LD]
-    double* V = sm + 2 * EJ_MAX * EJ_LD;      // [EJ_MAX][EJ_LD]
-    __shared__ double s_c[2][EJ_MAX / 2], s_s[2][EJ_MAX / 2];
+    extern __shared__ __align__(16) double sm[];
+    double* Ain = sm;                               // [EJ_MAX][EJ_LD] x 2 (A), x 2 (V)
+    double* Aout = sm + EJ_MAX * EJ_LD;
+    double* Vin = sm + 2 * EJ_MAX * EJ_LD;
+    double* Vout = sm + 3 * EJ_MAX * EJ_LD;
+    __shared__ double2 s_rot[2][EJ_MAX / 2];        // (c, s) of every pair, double buffered
+    __shared__ short s_perm[2][EJ_MAX];             // seat -> original index
     __shared__ int s_order[EJ_MAX];
-    __shared__ unsigned short s_sched[(EJ_MAX - 1) * (EJ_MAX / 2)];
-    __shared__ unsigned char s_slot[(EJ_MAX - 1) * EJ_MAX];    // step, index -> pair * 2 + (index is the pair's q)
+    __shared__ double s_sign[EJ_MAX];
+    __shared__ double s_floor;
 
-    const int M = (m + 1) & ~1;             // even number of players; index m (if any) is a dummy
+    const int M = (m + 1) & ~1;             // even number of players; original index m (if any) is a dummy
     const int npair = M / 2;
     for (int e = threadIdx.x; e < M * M; e += EJ_THREADS) {
         const int i = e / M, j = e - i * M;
@@ -99,142 +124,124 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
         // dummy player of an odd m is a zero row/column that only ever meets identity rotations
         double a = 0.0;
         if (i < m && j < m) a = (i <= j) ? G[i * m + j] : G[j * m + i];
-        A0[i * EJ_LD + j] = a;
-        V[i * EJ_LD + j] = (i == j) ? 1.0 : 0.0;
+        Ain[i * EJ_LD + j] = a;
+        Vin[i * EJ_LD + j] = (i == j) ? 1.0 : 0.0;
     }
+    if (threadIdx.x < M) s_perm[0][threadIdx.x] = (short)threadIdx.x;
     __syncthreads();
     // absolute floor for rotations: entries below eps^1.25 * max|a_ii| cannot move any eigenvalue
     // by more than that (the Gram of row-centred data is exactly rank deficient, and its null
     // direction would otherwise keep the relative criterion busy with rounding noise forever)
-    __shared__ double s_floor;
     if (threadIdx.x == 0) {
         double dmax = 0.0;
-        for (int i = 0; i < m; ++i) dmax = fmax(dmax, fabs(A0[i * EJ_LD + i]));
+        for (int i = 0; i < m; ++i) dmax = fmax(dmax, fabs(Ain[i * EJ_LD + i]));
         s_floor = dmax * 1.0e-20;
-    }
-    // round-robin schedule: pair i of step k, stored once (no integer division in the sweeps)
-    for (int e = threadIdx.x; e < (M - 1) * npair; e += EJ_THREADS) {
-        const int step = e / npair, i = e - step * npair;
-        int p, q;
-        if (i == 0) { p = M - 1; q = step; }
-        else { p = (step + i) % (M - 1); q = (step - i + (M - 1)) % (M - 1); }
-        if (p > q) { const int tswap = p; p = q; q = tswap; }
-        s_sched[e] = (unsigned short)((p << 8) | q);
-        s_slot[step * M + p] = (unsigned char)(2 * i);
-        s_slot[step * M + q] = (unsigned char)(2 * i + 1);
     }
     __syncthreads();
     const double floor_abs = s_floor, big_abs = s_floor * 1.0e7;      // 1e-13 * max|a_ii|
 
     // fixed work items of this thread (at most two: 2 * npair^2 <= 2048 items, 1024 threads)
     const int nblk = npair * npair, nitem = 2 * nblk;
-    int it_i[2], it_j[2];                    // A item: (i, j);  V item: (npair + pair i, row pair j)
+    int it_i[2], it_j[2], it_d0[2], it_d1[2], it_d2[2], it_d3[2];
     for (int k = 0; k < 2; ++k) {
         const int e = threadIdx.x + k * EJ_THREADS;
         it_i[k] = it_j[k] = -1;
-        if (e < nblk) { it_i[k] = e / npair; it_j[k] = e - it_i[k] * npair; }
-        else if (e < nitem) { const int u = e - nblk; it_j[k] = u / npair; it_i[k] = npair + (u - it_j[k] * npair); }
+        it_d0[k] = it_d1[k] = it_d2[k] = it_d3[k] = 0;
+        if (e < nblk) {                       // A item: block (i, j) -> seats (next(2i), next(2i+1)) x (next(2j), next(2j+1))
+            const int i = e / npair, j = e - i * npair;
+            it_i[k] = i; it_j[k] = j;
+            const int r0 = seat_next(2 * i, npair), r1 = seat_next(2 * i + 1, npair);
+            const int c0 = seat_next(2 * j, npair), c1 = seat_next(2 * j + 1, npair);
+            it_d0[k] = r0 * EJ_LD + c0; it_d1[k] = r0 * EJ_LD + c1;
+            it_d2[k] = r1 * EJ_LD + c0; it_d3[k] = r1 * EJ_LD + c1;
+        } else if (e < nitem) {               // V item: rows (2 rp, 2 rp + 1), pair i -> column seats of pair i
+            const int u = e - nblk, rp = u / npair, i = u - rp * npair;
+            it_i[k] = npair + i; it_j[k] = rp;
+            const int c0 = seat_next(2 * i, npair), c1 = seat_next(2 * i + 1, npair);
+            it_d0[k] = (2 * rp) * EJ_LD + c0; it_d1[k] = (2 * rp) * EJ_LD + c1;
+            it_d2[k] = (2 * rp + 1) * EJ_LD + c0; it_d3[k] = (2 * rp + 1) * EJ_LD + c1;
+        }
     }
-    const int la = EJ_THREADS - 1 - (int)threadIdx.x;                // look-ahead pair of this thread (if < npair)
+    // look-ahead: pair `la` of the next step sits at seats (2 la, 2 la + 1) then, i.e. at x, y now
+    const int la = EJ_THREADS - 1 - (int)threadIdx.x;
+    const bool is_la = la < npair;
+    const int lx = seat_prev(2 * (is_la ? la : 0), npair), ly = seat_prev(2 * (is_la ? la : 0) + 1, npair);
+    const int kx = lx >> 1, rx = lx & 1, ky = ly >> 1, ry = ly & 1;
 
     // rotations of the very first step
-    if (la < npair) {
-        const int p = s_sched[la] >> 8, q = s_sched[la] & 255;
+    int b0 = 0;
+    if (is_la) {
         double c = 1.0, s = 0.0;
         bool big = false;
-        if (q < m) jacobi_rot(A0[p * EJ_LD + q], A0[p * EJ_LD + p], A0[q * EJ_LD + q], floor_abs, big_abs, c, s, big);
-        s_c[0][la] = c; s_s[0][la] = s;
+        if (2 * la + 1 < m)                 // seats == original indices before the first move; index m is the dummy
+            jacobi_rot(Ain[(2 * la) * EJ_LD + 2 * la + 1], Ain[(2 * la) * EJ_LD + 2 * la],
+                       Ain[(2 * la + 1) * EJ_LD + 2 * la + 1], floor_abs, big_abs, c, s, big);
+        s_rot[0][la] = make_double2(c, s);
+        b0 = big ? 1 : 0;
     }
-    __syncthreads();
+    int big_next = __syncthreads_or(b0);    // a big rotation among those prepared for the coming step (uniform)
 
-    double* Ain = A0;
-    double* Aout = A1;
     int sweep = 0, par = 0;
-    int big_next = 0;            // a big rotation among those prepared for the coming step (uniform)
-    {
-        // the first step's own "big" flags: recompute cheaply from its rotations being non-trivial is not
-        // equivalent, so evaluate the criterion once more for step 0 (only here, outside the loop)
-        int b0 = 0;
-        if (la < npair) {
-            const int p = s_sched[la] >> 8, q = s_sched[la] & 255;
-            if (q < m) {
-                const double apq = A0[p * EJ_LD + q], den = fabs(A0[p * EJ_LD + p] * A0[q * EJ_LD + q]);
-                b0 = (apq * apq > 1.0e-18 * den && fabs(apq) > big_abs) ? 1 : 0;
-            }
-        }
-        big_next = __syncthreads_or(b0);
-    }
     for (; sweep < EJ_MAX_SWEEPS; ++sweep) {
         int sweep_big = 0;
         for (int step = 0; step < M - 1; ++step) {
             sweep_big |= big_next;
-            const unsigned short* sched = s_sched + step * npair;
-            const double* cc = s_c[par];
-            const double* ss = s_s[par];
+            const double2* rot = s_rot[par];
             // 1. apply this step's rotations
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (it_i[k] < 0) continue;
                 if (it_i[k] < npair) {
-                    const int i = it_i[k], j = it_j[k];
-                    const int pi = sched[i] >> 8, qi = sched[i] & 255, pj = sched[j] >> 8, qj = sched[j] & 255;
-                    const Blk o = jacobi_block(Ain, pi, qi, pj, qj, cc[i], ss[i], cc[j], ss[j]);
-                    Aout[pi * EJ_LD + pj] = o.b00; Aout[pi * EJ_LD + qj] = o.b01;
-                    Aout[qi * EJ_LD + pj] = o.b10; Aout[qi * EJ_LD + qj] = o.b11;
+                    const Blk o = jacobi_block(Ain, it_i[k], it_j[k], rot[it_i[k]], rot[it_j[k]]);
+                    Aout[it_d0[k]] = o.b00; Aout[it_d1[k]] = o.b01;
+                    Aout[it_d2[k]] = o.b10; Aout[it_d3[k]] = o.b11;
                 } else {
                     const int i = it_i[k] - npair, r0 = 2 * it_j[k];
-                    const double s = ss[i];
-                    if (s != 0.0) {
-                        const double c = cc[i];
-                        const int p = sched[i] >> 8, q = sched[i] & 255;
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int row = r0 + rr;
-                            const double vp = V[row * EJ_LD + p], vq = V[row * EJ_LD + q];
-                            V[row * EJ_LD + p] = c * vp - s * vq;
-                            V[row * EJ_LD + q] = s * vp + c * vq;
-                        }
-                    }
+                    const double2 cs = rot[i];
+                    const double2 v0 = *reinterpret_cast<const double2*>(Vin + r0 * EJ_LD + 2 * i);
+                    const double2 v1 = *reinterpret_cast<const double2*>(Vin + (r0 + 1) * EJ_LD + 2 * i);
+                    Vout[it_d0[k]] = cs.x * v0.x - cs.y * v0.y; Vout[it_d1[k]] = cs.y * v0.x + cs.x * v0.y;
+                    Vout[it_d2[k]] = cs.x * v1.x - cs.y * v1.y; Vout[it_d3[k]] = cs.y * v1.x + cs.x * v1.y;
                 }
             }
-            // 2. look-ahead: the rotation of pair `la` of the NEXT step from the entries it will see
+            // 2. seats -> original indices follow the players
+            if (threadIdx.x < M) s_perm[par ^ 1][seat_next(threadIdx.x, npair)] = s_perm[par][threadIdx.x];
+            // 3. look-ahead: the rotation of pair `la` of the NEXT step from the entries it will see
             int my_big = 0;
-            if (la < npair) {
-                const int nstep = (step + 1 == M - 1) ? 0 : step + 1;
-                const unsigned short pq = s_sched[nstep * npair + la];
-                const int p = pq >> 8, q = pq & 255;
+            if (is_la) {
                 double c = 1.0, s = 0.0;
                 bool big = false;
-                if (q < m) {
-                    const unsigned char* slot = s_slot + step * M;
-                    const int ip = slot[p] >> 1, rp = slot[p] & 1, iq = slot[q] >> 1, rq = slot[q] & 1;
-                    const int ppi = sched[ip] >> 8, qpi = sched[ip] & 255, ppq = sched[iq] >> 8, qpq = sched[iq] & 255;
-                    const double cip = cc[ip], sip = ss[ip], ciq = cc[iq], siq = ss[iq];
-                    const Blk bpq = jacobi_block(Ain, ppi, qpi, ppq, qpq, cip, sip, ciq, siq);
-                    const Blk bpp = jacobi_block(Ain, ppi, qpi, ppi, qpi, cip, sip, cip, sip);
-                    const Blk bqq = jacobi_block(Ain, ppq, qpq, ppq, qpq, ciq, siq, ciq, siq);
-                    const double apq = rp ? (rq ? bpq.b11 : bpq.b10) : (rq ? bpq.b01 : bpq.b00);
-                    const double app = rp ? bpp.b11 : bpp.b00;
-                    const double aqq = rq ? bqq.b11 : bqq.b00;
+                if (s_perm[par][lx] < m && s_perm[par][ly] < m) {
+                    const double2 rkx = rot[kx], rky = rot[ky];
+                    const Blk bpq = jacobi_block(Ain, kx, ky, rkx, rky);
+                    const Blk bpp = jacobi_block(Ain, kx, kx, rkx, rkx);
+                    const Blk bqq = jacobi_block(Ain, ky, ky, rky, rky);
+                    const double apq = rx ? (ry ? bpq.b11 : bpq.b10) : (ry ? bpq.b01 : bpq.b00);
+                    const double app = rx ? bpp.b11 : bpp.b00;
+                    const double aqq = ry ? bqq.b11 : bqq.b00;
                     jacobi_rot(apq, app, aqq, floor_abs, big_abs, c, s, big);
                 }
-                s_c[par ^ 1][la] = c; s_s[par ^ 1][la] = s;
+                s_rot[par ^ 1][la] = make_double2(c, s);
                 my_big = big ? 1 : 0;
             }
             big_next = __syncthreads_or(my_big);
             double* tsw = Ain; Ain = Aout; Aout = tsw;
+            tsw = Vin; Vin = Vout; Vout = tsw;
             par ^= 1;
         }
         if (!sweep_big) break;
     }
     const double* A = Ain;
+    const double* V = Vin;
+    const short* perm = s_perm[par];
 
-    // descending order by rank counting (ties broken by index)
-    if (threadIdx.x < m) {
+    // descending order by rank counting over the seats of real players (ties broken by seat)
+    if (threadIdx.x < M && perm[threadIdx.x] < m) {
         const int i = threadIdx.x;
         const double wi = A[i * EJ_LD + i];
         int rank = 0;
-        for (int j = 0; j < m; ++j) {
+        for (int j = 0; j < M; ++j) {
+            if (perm[j] >= m) continue;
             const double wj = A[j * EJ_LD + j];
             rank += (wj > wi) || (wj == wi && j < i);
         }
@@ -243,7 +250,6 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
     __syncthreads();
     if (threadIdx.x < m) w_out[threadIdx.x] = A[s_order[threadIdx.x] * EJ_LD + s_order[threadIdx.x]];
     // deterministic sign: the largest-magnitude component of every eigenvector is positive
-    __shared__ double s_sign[EJ_MAX];
     if (threadIdx.x < m) {
         const int col = s_order[threadIdx.x];
         double best = -1.0, sg = 1.0;
@@ -270,7 +276,7 @@ extern "C" int omb_eigh_jacobi(const double* d_G, int64_t m, double* d_w, double
     using namespace omb;
     OMB_CHECK_ARG(d_G && d_w && d_V, "null pointer");
     OMB_CHECK_ARG(m >= 1 && m <= EJ_MAX, "m must be in [1, 64]");
-    const size_t smem = sizeof(double) * 3 * EJ_MAX * EJ_LD;
+    const size_t smem = sizeof(double) * 4 * EJ_MAX * EJ_LD;
     OMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eigh_jacobi_kernel<<<1, EJ_THREADS, smem, (cudaStream_t)stream>>>(d_G, (int)m, d_w, d_V, d_info);
     return check_launch("eigh_jacobi_kernel");
