@@ -153,6 +153,16 @@ int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s, const doub
                  const void* d_peers, double* d_mine, int64_t epoch, int64_t* d_piv, double* d_rdiag,
                  double* d_gap, void* stream);
 
+/* ---- multi-GPU plumbing: all-gather of a small FP64 payload over NVLink peer memory (replaces an
+ *      NCCL all-gather for the F*4 statistics, the m x m Gram and the sensor rows).
+ *      d_peers: device array of `world` symmetric-buffer addresses (entry `rank` == d_mine), each
+ *      omb_p2p_allgather_buffer_doubles(world, capacity) doubles, zero-filled once.  seq: strictly
+ *      increasing per call, identical on every rank.  d_out: world x n, rank order. */
+int64_t omb_p2p_allgather_buffer_doubles(int world, int64_t capacity);
+int64_t omb_p2p_allgather_error_index(int world, int64_t capacity);
+int omb_p2p_allgather(const double* d_src, int64_t n, double* d_out, const void* d_peers, double* d_mine,
+                      int64_t capacity, int64_t seq, int rank, int world, void* stream);
+
 /* ---- GEM: greedy entropy-maximisation placement (SPR.gem, sparse_sensing.py:586-698; reached via
  *      optimal_placement(calc_type='gem') :745-751).  One streaming pass over the basis per sensor.
  *      omb_gem_variance: d_var[j] = np.var(Ur[j, :], ddof=1)                              (:621, :639)

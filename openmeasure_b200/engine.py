@@ -177,7 +177,9 @@ class Engine:
             idx = torch.argmax(V.abs(), dim=0)
             sgn = torch.sign(V[idx, torch.arange(m, device=V.device)])
             V = (V * torch.where(sgn == 0, torch.ones_like(sgn), sgn)).contiguous()
-        if self.world > 1:                          # every rank must rotate with the very same V
+        if self.world > 1 and m > int(_lib.load().omb_eigh_max_m()):
+            # library eigensolver: every rank must rotate with the very same V.  (The one-CTA Jacobi
+            # kernel is deterministic and its input G is bit-identical on every rank: no broadcast.)
             w = self.comm.bcast(w.contiguous(), 0)
             V = self.comm.bcast(V.contiguous(), 0)
         return torch.sqrt(torch.clamp(w, min=0.0)), V
