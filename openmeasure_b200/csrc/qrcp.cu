@@ -951,7 +951,12 @@ namespace omb {
 static int64_t gemv_grid(int64_t n)
 {
     int64_t g = ceil_div(basis_tiles(n) * (OMB_TB / 2), GV_THREADS);
-    const int64_t cap = (int64_t)sm_count() * 8;
+    static int per_sm = 0;                     // a whole number of waves of resident CTAs: no straggler CTAs
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_gemv_kernel, GV_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+        per_sm *= 2;                           // two whole waves (measured: 2.77 ms vs 2.82 ms for one or three)
+    }
+    const int64_t cap = (int64_t)sm_count() * per_sm;
     if (g > cap) g = cap;
     if (g > QR_NCAND) g = QR_NCAND;
     return g;
