@@ -521,19 +521,6 @@ static ApplyMmaFn pick_apply_mma(int L, int* ng)
 // ---------------------------------------------------------------------------------------------
 constexpr int PN_THREADS = 256;
 
-__device__ __forceinline__ double block_sum(double x, double* s_red)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) s_red[warp] = x;
-    __syncthreads();
-    double s = 0.0;
-    for (int w = 0; w < PN_THREADS / 32; ++w) s += s_red[w];
-    return s;
-}
-
 // ---- peer-to-peer exchange over NVLink (symmetric memory): every rank owns a buffer laid out as
 //   LL slots [2 parity][world][2 * QR_REC] u64 | (reserved [2][world]) | barrier flags [world] i64 | error i64
 // and holds the device addresses of all ranks' buffers.  A record travels in the low-latency format
