@@ -227,6 +227,28 @@ class Engine:
         _lib.call("omb_modes_to_rows", _p(self.Ut), self.n_loc, self.r, _p(out), _stream())
         return out
 
+    def basis_gram(self):
+        """H = U_r^T U_r (r x r) of the installed basis, identical on every rank: the basis is laid out as
+        rows once and goes through the same Gram kernels as the snapshots."""
+        U1 = self.basis_rows()
+        r = self.r
+        Gf = torch.empty(r * r, dtype=torch.float64, device=self.dev)
+        ws = _ws(_lib.load().omb_gram_ws_bytes(1, self.n_loc, r), self.dev)
+        _lib.call("omb_gram", _p(U1), 1, self.n_loc, r, None, _p(Gf), _p(ws), _stream())
+        H = Gf.view(r, r)
+        if self.world > 1:
+            H = _comm.ordered_sum(self.comm.allgather(H.contiguous())).view(r, r)
+        return H, U1
+
+    def basis_rotate(self, U1, M):
+        """Install U_r <- U1 M (M: r x r) as the basis, with fresh placement norms (the back-projection
+        kernel with U1 in the role of the snapshots)."""
+        r = self.r
+        Ut = self._new_basis(r)
+        vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_backproject", _p(U1), 1, self.n_loc, r, None, None, _p(M.contiguous()), r, _p(Ut), _p(vn), _stream())
+        self.Ut, self.vn = Ut, vn
+
     def mask_rows(self, mask_dev):
         """optimal_placement(mask=...): zero the excluded rows of the basis in place (:737-738)."""
         keep = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev)

@@ -90,6 +90,12 @@ class ROM:
     """Reduced-order-model utilities: centring/scaling, POD, truncation, reconstruction
     (reference ROM, sparse_sensing.py:18-511)."""
 
+    # POD accuracy control (extension): the Gram route resolves sigma_r to eps (sigma_1/sigma_r)^2;
+    # when that estimate exceeds pod_refine_tol a CholeskyQR2-style correction of the basis (two
+    # more passes over the n x r modes) brings it to eps sigma_1/sigma_r.  'auto' | True | False.
+    pod_refine = 'auto'
+    pod_refine_tol = 1e-11
+
     def __init__(self, X, n_features, xyz):
         if type(X) is not np.ndarray:                     # :69-70
             raise TypeError('The matrix X is not a numpy array.')
@@ -310,17 +316,48 @@ class ROM:
         safe = Sr > S[0] * (eng.m * _eng.EPS)
         W = torch.where(safe, 1.0 / torch.where(safe, Sr, torch.ones_like(Sr)), torch.zeros_like(Sr))
         eng.backproject((V[:, :r] * W).contiguous(), centred=centred, scaled=scaled)
-        Ar_d = V[:, :r] * Sr                                  # A = V Sigma (:273)
         if S_h is None:
             S_h = S.cpu().numpy()
+        S_h = S_h.copy()
+        Vr_h = V[:, :r].cpu().numpy()
+        # smallest retained singular value that carries information (the numerically-zero mode of
+        # row-centred data, back-projected with a zero weight, is excluded from the accuracy estimate)
+        live = S_h[:r][S_h[:r] > S_h[0] * (eng.m * _eng.EPS)]
+        s_min = float(live[-1]) if live.size else float(S_h[0])
+        bound = float(_eng.EPS * (S_h[0] / s_min) ** 2) if s_min > 0 else 0.0
+        self.pod_refined = False
+        if self.pod_refine is True or (self.pod_refine == 'auto' and bound > self.pod_refine_tol):
+            # The Gram route loses eps (sigma_1/sigma_r)^2.  One CholeskyQR2-style correction on the
+            # basis itself brings that down to eps sigma_1/sigma_r:  U1 = X0 V_r S^-1 = P S1 Q^T
+            # (from H = U1^T U1 = Q S1^2 Q^T);  X0 V_r = P (S1 Q^T S) = P B;  SVD B = A1 S2 A2^T  =>
+            # U = U1 (Q S1^-1 A1),  sigma = S2,  V = V_r A2.  Two extra passes over the n x r basis.
+            H, U1 = eng.basis_gram()
+            lam1, Q1 = np.linalg.eigh(H.cpu().numpy())
+            S1 = np.sqrt(np.maximum(lam1, 0.0))
+            ok = S1 > 0
+            B = (S1[:, None] * Q1.T) * S_h[:r][None, :]
+            A1, S2, A2t = np.linalg.svd(B)
+            M = (Q1 * np.where(ok, 1.0 / np.where(ok, S1, 1.0), 0.0)[None, :]) @ A1
+            Vn = Vr_h @ A2t.T
+            sgn = np.sign(Vn[np.argmax(np.abs(Vn), axis=0), np.arange(r)])
+            sgn[sgn == 0] = 1.0
+            Vr_h, M = Vn * sgn, M * sgn
+            eng.basis_rotate(U1, torch.from_numpy(np.ascontiguousarray(M)).to(eng.dev))
+            S_h[:r] = S2
+            live = S2[S2 > S2[0] * (eng.m * _eng.EPS)]
+            bound = float(_eng.EPS * S2[0] / live[-1]) if live.size else 0.0
+            self.pod_refined = True
         lam = S_h ** 2
         exp_variance = 100 * np.cumsum(lam) / np.sum(lam)     # :274-275
-        Ar = Ar_d.cpu().numpy()
+        Ar = Vr_h * S_h[:r]                                   # A = V Sigma (:273)
         self.r = r
         self._host.pop("Ur", None)
         self.pod_sigma = S_h
-        with np.errstate(over="ignore", divide="ignore"):
-            self.pod_rel_err_bound = float(_eng.EPS * (S_h[0] / max(S_h[r - 1], 1e-300)) ** 2)
+        self.pod_rel_err_bound = bound
+        if bound > 1e-10:
+            import warnings
+            warnings.warn("POD: estimated relative error of the smallest retained singular value is %.1e "
+                          "(sigma_r/sigma_1 = %.1e)" % (bound, S_h[r - 1] / S_h[0]), RuntimeWarning)
         return Ar, exp_variance[:r]
 
     def decomposition(self, X0, select_modes='variance', n_modes=99):

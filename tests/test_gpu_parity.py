@@ -642,3 +642,33 @@ def test_full_size_properties(torch_cuda, F, n_c, m, r):
     del U
     xr = eng.reconstruct(torch.from_numpy(a).to(Xd.device))[:, 0]
     assert float((xr - x).abs().max() / x.abs().max()) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# POD accuracy on a graded spectrum (sigma_r / sigma_1 = 1e-5): the Gram route alone resolves the
+# smallest singular values to ~1e-6; the CholeskyQR2-style basis correction restores 1e-10
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,r", [(6000, 16, 12), (4000, 96, 40)])
+def test_pod_refinement_graded_spectrum(torch_cuda, n, m, r):
+    sps = _sps()
+    rng = np.random.default_rng(n + m)
+    Uo, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    Vo, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    sig = np.concatenate([np.logspace(0, -5, r), np.logspace(-5.5, -7, m - r)])
+    X0 = (Uo * sig) @ Vo.T
+    Uref, Sref, Vtref = np.linalg.svd(X0, full_matrices=False)
+    rom = sps.ROM(X0, 1, None)
+    rom.pod_refine = False
+    _, _, _ = rom.decomposition(X0, 'number', r)
+    err_gram = np.max(np.abs(rom.pod_sigma[:r] - Sref[:r]) / Sref[:r])
+    rom.pod_refine = 'auto'
+    Ur, Ar, ev = rom.decomposition(X0, 'number', r)
+    assert rom.pod_refined and rom.pod_rel_err_bound < 1e-10
+    S = np.linalg.norm(Ar, axis=0)
+    err_ref = np.max(np.abs(S - Sref[:r]) / Sref[:r])
+    assert err_ref < 1e-10 < err_gram, (err_ref, err_gram)
+    np.testing.assert_allclose(Ur.T @ Ur, np.eye(r), atol=1e-12)
+    Ua, s = _sign_align(Ur, Uref[:, :r])
+    # modes up to sign; the smallest ones are determined to eps * sigma_1 / (gap to the neighbours)
+    np.testing.assert_allclose(Ua[:, : r // 2], Uref[:, : r // 2], atol=1e-9)
+    np.testing.assert_allclose(Ur @ Ar.T, (Uref[:, :r] * Sref[:r]) @ Vtref[:r], atol=1e-10 * Sref[0])
