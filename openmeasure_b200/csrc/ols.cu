@@ -201,6 +201,133 @@ ols_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, int6
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Reconstruct, TMA-pipelined (even r, even N, row range aligned to basis tiles): persistent CTAs
+// walk 128 x 128 output tiles (one basis tile of candidates x 128 coefficient vectors).  A 32-mode
+// K-chunk of the basis tile is 32 contiguous 1 KB rows of the tiled layout (one bulk copy each, pitch
+// 132 doubles), the matching chunk of the coefficient rows 128 copies of 256 bytes (pitch 36): both
+// operands land bank-conflict free.  3-stage ring, every warp issues its share two chunks ahead and
+// across tile boundaries; 8 warps own 32 x 64 outputs each (64 DMMA accumulators per lane); the
+// epilogue scl * acc + cnt (two roundings, like the reference's multiply-then-add) goes out as
+// 16-byte stores.  FP64-tensor bound: 2 n r N flop against 8 n N written bytes (r/4 flop per byte).
+// ---------------------------------------------------------------------------------------------
+constexpr int RB_K = 32;
+constexpr int RB_LDA = OMB_TB + 4;          // [k][i]: == 4 (mod 16)
+constexpr int RB_LDB = RB_K + 4;            // [j][k]: == 4 (mod 16)
+constexpr int RB_STAGES = 3;
+constexpr int RB_THREADS = 256;
+constexpr int RB_STAGE = RB_K * RB_LDA + OMB_TB * RB_LDB;
+static size_t reconstruct_big_smem() { return sizeof(double) * (size_t)RB_STAGES * RB_STAGE; }
+
+__global__ void __launch_bounds__(RB_THREADS)
+reconstruct_big_kernel(const double* __restrict__ Ut, int r, const double* __restrict__ Ac, int64_t N,
+                       const double* __restrict__ cnt, const double* __restrict__ scl, int64_t n_c, int64_t row0,
+                       int64_t nrows, double* __restrict__ out)
+{
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[RB_STAGES], empty_bar[RB_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tiles_i = ceil_div(nrows, (int64_t)OMB_TB), tiles_j = ceil_div(N, (int64_t)OMB_TB);
+    const int64_t ntiles = tiles_i * tiles_j;
+    const int nch = (r + RB_K - 1) / RB_K;
+    const int64_t tile0 = row0 / OMB_TB;                     // row0 is a multiple of 128
+
+    for (int e = threadIdx.x; e < RB_STAGES * RB_STAGE; e += RB_THREADS) smem[e] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RB_STAGES; ++s) { mbar_init(&full_bar[s], RB_THREADS / 32); mbar_init(&empty_bar[s], RB_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- issue side: this warp's share (4 mode rows of the basis tile, 16 coefficient rows) of chunk gi
+    int64_t it_tile = blockIdx.x, gi = 0;
+    int it_c = 0;
+    auto issue = [&]() {
+        if (it_tile >= ntiles) return;
+        const int s = (int)(gi % RB_STAGES);
+        if (gi >= RB_STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((gi / RB_STAGES) - 1) & 1));
+        const int64_t ti = it_tile / tiles_j, tj = it_tile - ti * tiles_j;
+        const int k0 = it_c * RB_K;
+        const int kv = (r - k0) < RB_K ? (r - k0) : RB_K;
+        const int64_t j0 = tj * OMB_TB;
+        const int jv = (int)((N - j0) < OMB_TB ? (N - j0) : OMB_TB);
+        int na = kv - 4 * warp; na = na < 0 ? 0 : (na > 4 ? 4 : na);
+        int nb = jv - 16 * warp; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+        double* sA = smem + (size_t)s * RB_STAGE;
+        double* sB = sA + RB_K * RB_LDA;
+        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(((int64_t)na * OMB_TB + (int64_t)nb * kv) * sizeof(double)));
+        __syncwarp();
+        if (lane < na) {
+            const int kk = 4 * warp + lane;
+            tma_load_bulk(sA + kk * RB_LDA, Ut + (tile0 + ti) * ((int64_t)r * OMB_TB) + (int64_t)(k0 + kk) * OMB_TB,
+                          OMB_TB * sizeof(double), &full_bar[s]);
+        } else if (lane >= 16 && lane - 16 < nb) {
+            const int jj = 16 * warp + lane - 16;
+            tma_load_bulk(sB + jj * RB_LDB, Ac + (j0 + jj) * r + k0, (uint32_t)(kv * sizeof(double)), &full_bar[s]);
+        }
+        ++gi;
+        if (++it_c == nch) { it_c = 0; it_tile += gridDim.x; }
+    };
+#pragma unroll 1
+    for (int u = 0; u < RB_STAGES - 1; ++u) issue();
+
+    const int fr = lane & 3, fc = lane >> 2;
+    const int ib = (warp >> 1) * 32, jb = (warp & 1) * 64;
+    int64_t g = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t ti = tile / tiles_j, tj = tile - ti * tiles_j;
+        double acc[4][8][2];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[p][q][0] = acc[p][q][1] = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, ++g) {
+            issue();
+            const int s = (int)(g % RB_STAGES);
+            mbar_wait(&full_bar[s], (uint32_t)((g / RB_STAGES) & 1));
+            const double* sA = smem + (size_t)s * RB_STAGE;
+            const double* sB = sA + RB_K * RB_LDA;
+            const int kv = (r - c * RB_K) < RB_K ? (r - c * RB_K) : RB_K;
+#pragma unroll
+            for (int k4 = 0; k4 < RB_K / 4; ++k4) {
+                const int kk = k4 * 4 + fr;
+                const bool kok = kk < kv;                      // stale modes of a ragged last chunk
+                double a[4], b[8];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = sA[kk * RB_LDA + ib + 8 * p + fc];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = sB[(jb + 8 * q + fc) * RB_LDB + kk];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = kok ? a[p] : 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dmma884(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        }
+        // epilogue: x = scl * acc + cnt, 16-byte stores (N even, j even)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int64_t i = ti * OMB_TB + ib + 8 * p + fc;         // row inside the requested range
+            if (i >= nrows) continue;
+            const double sc = scl ? scl[(row0 + i) / n_c] : 1.0;
+            const double cn = cnt ? cnt[row0 + i] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t j = tj * OMB_TB + jb + 8 * q + 2 * fr;
+                if (j >= N) continue;
+                double v0 = sc * acc[p][q][0], v1 = sc * acc[p][q][1];
+                v0 = v0 + cn; v1 = v1 + cn;
+                stg_stream2(out + i * N + j, make_double2(v0, v1));
+            }
+        }
+    }
+}
+
 }  // namespace omb
 
 using namespace omb;
@@ -260,6 +387,16 @@ extern "C" int omb_reconstruct(const double* d_Ut, int64_t n, int64_t r, const d
     OMB_CHECK_ARG(d_Ut && d_A && d_out, "null pointer");
     OMB_CHECK_ARG(N > 0 && r > 0 && nrows > 0 && row0 >= 0 && n_c > 0 && r < (1 << 24), "bad size");
     OMB_CHECK_ARG(row0 + nrows <= n, "row range exceeds n");
+    if ((r & 1) == 0 && (N & 1) == 0 && row0 % OMB_TB == 0 && r >= 16 && N >= 16 &&
+        ((reinterpret_cast<uintptr_t>(d_Ut) | reinterpret_cast<uintptr_t>(d_A) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0) {
+        OMB_CUDA(cudaFuncSetAttribute(reconstruct_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)reconstruct_big_smem()));
+        int64_t g = ceil_div(nrows, (int64_t)OMB_TB) * ceil_div(N, (int64_t)OMB_TB);
+        if (g > sm_count()) g = sm_count();
+        reconstruct_big_kernel<<<(unsigned)g, RB_THREADS, reconstruct_big_smem(), (cudaStream_t)stream>>>(
+            d_Ut, (int)r, d_A, N, d_cnt, d_scl, n_c, row0, nrows, d_out);
+        return check_launch("reconstruct_big_kernel");
+    }
     int64_t tiles = ceil_div(nrows, OT) * ceil_div(N, OT);
     if (tiles > (int64_t)sm_count() * 8) tiles = (int64_t)sm_count() * 8;
     ols_gemm_kernel<1><<<(unsigned)tiles, O_THREADS, 0, (cudaStream_t)stream>>>(d_Ut, d_A, nrows, N, (int)r, 0, d_cnt,

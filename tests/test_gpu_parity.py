@@ -672,3 +672,25 @@ def test_pod_refinement_graded_spectrum(torch_cuda, n, m, r):
     # modes up to sign; the smallest ones are determined to eps * sigma_1 / (gap to the neighbours)
     np.testing.assert_allclose(Ua[:, : r // 2], Uref[:, : r // 2], atol=1e-9)
     np.testing.assert_allclose(Ur @ Ar.T, (Uref[:, :r] * Sref[:r]) @ Vtref[:r], atol=1e-10 * Sref[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# batched reconstruct across the kernel-selection boundary (TMA-pipelined 128 x 128 tiles for even
+# r / N, staged 64 x 64 tiles otherwise), ragged row and vector counts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_c,r,N", [(700, 10, 7), (1000, 16, 16), (3001, 40, 130), (2050, 100, 64), (900, 14, 258)])
+def test_batched_reconstruct_matches_numpy(torch_cuda, n_c, r, N):
+    torch = torch_cuda
+    from openmeasure_b200 import engine as E
+    F, m = 2, max(r + 4, 24)
+    rng = np.random.default_rng(n_c + r + N)
+    X = rng.random((F * n_c, m)) + 1.0
+    eng = E.Engine(torch.from_numpy(X).cuda(), F, group=False)
+    eng.stats("std", 1)
+    Ur = rng.standard_normal((F * n_c, r))
+    eng.set_basis_rows(torch.from_numpy(Ur).cuda())
+    A = rng.standard_normal((N, r))
+    got = eng.reconstruct(torch.from_numpy(A).cuda()).cpu().numpy()
+    scl = np.repeat(eng.scl.cpu().numpy(), n_c)[:, None]
+    ref = scl * (Ur @ A.T) + eng.cnt.cpu().numpy()[:, None]
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
