@@ -97,6 +97,7 @@ class Engine:
     def cnt(self):
         """Centring value per local row; flushes row means deferred to the Gram pass."""
         if self._cnt_pending:
+            self._wait_arrival()
             _lib.call("omb_row_means", _p(self.X), self.n_loc, self.m, _p(self._cnt), _stream())
             self._cnt_pending = False
         return self._cnt
@@ -104,6 +105,15 @@ class Engine:
     @cnt.setter
     def cnt(self, v):
         self._cnt, self._cnt_pending = v, False
+
+    def _wait_arrival(self):
+        """X may still be in flight from the host (ROM._engine uploads it block by block): make the
+        current stream wait for all of it.  stats() consumes the blocks one by one instead."""
+        arrival = getattr(self, "_arrival", None)
+        if arrival is not None:
+            for ev in arrival:
+                torch.cuda.current_stream().wait_event(ev)
+            self._arrival = None
 
     def _shard_args(self):
         return (self.n_c_loc, self.n_c, self.cell0, self.rank, self.world)
@@ -121,19 +131,50 @@ class Engine:
         blk = ncl * m
         ws = _ws(_lib.load().omb_block_stats_ws_bytes(F, blk), self.dev)
         pending = False
-        if axis_cnt == 1:
-            if defer_row_means:
-                pending = True
-            else:
-                _lib.call("omb_row_means", _p(self.X), self.n_loc, m, _p(cnt), st)
         count = self.n_c * m
-        _lib.call("omb_block_stats", _p(self.X), F, blk, 0, count, _p(stats), _p(ws), st)
-        if self.world > 1:
-            stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=False)
-        if scale_type in NEEDS_SQDEV:
-            _lib.call("omb_block_stats", _p(self.X), F, blk, 1, count, _p(stats), _p(ws), st)
+        self._Gf_cached = None
+        arrival = getattr(self, "_arrival", None)
+        if arrival is not None and self.world == 1:
+            # X is still on its way from the host, one feature block at a time (ROM._engine): run every
+            # pass of this stage on a block as soon as it has landed -- the statistics and, when the
+            # caller defers the row means, the Gram pass hide behind the PCIe copy of the next blocks
+            self._arrival = None
+            L = _lib.load()
+            ws1 = _ws(L.omb_block_stats_ws_bytes(1, blk), self.dev)
+            fuse_gram = defer_row_means and axis_cnt == 1
+            if fuse_gram:
+                Gf = torch.empty(F * m * m, dtype=torch.float64, device=self.dev)
+                gws = _ws(L.omb_gram_ws_bytes(1, ncl, m), self.dev)
+            cur = torch.cuda.current_stream()
+            for f in range(F):
+                cur.wait_event(arrival[f])
+                Xf, sf, cf = self.X[f * ncl:(f + 1) * ncl], stats[4 * f:4 * f + 4], cnt[f * ncl:(f + 1) * ncl]
+                _lib.call("omb_block_stats", _p(Xf), 1, blk, 0, count, _p(sf), _p(ws1), st)
+                if scale_type in NEEDS_SQDEV:
+                    _lib.call("omb_block_stats", _p(Xf), 1, blk, 1, count, _p(sf), _p(ws1), st)
+                if fuse_gram:
+                    _lib.call("omb_gram_rowmeans", _p(Xf), 1, ncl, m, _p(cf), _p(Gf[f * m * m:(f + 1) * m * m]), _p(gws), st)
+                elif axis_cnt == 1:
+                    _lib.call("omb_row_means", _p(Xf), ncl, m, _p(cf), st)
+            if fuse_gram:
+                self._Gf_cached = Gf
+        else:
+            if arrival is not None:                         # multi-rank: wait for the whole shard
+                for ev in arrival:
+                    torch.cuda.current_stream().wait_event(ev)
+                self._arrival = None
+            if axis_cnt == 1:
+                if defer_row_means:
+                    pending = True
+                else:
+                    _lib.call("omb_row_means", _p(self.X), self.n_loc, m, _p(cnt), st)
+            _lib.call("omb_block_stats", _p(self.X), F, blk, 0, count, _p(stats), _p(ws), st)
             if self.world > 1:
-                stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=True)
+                stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=False)
+            if scale_type in NEEDS_SQDEV:
+                _lib.call("omb_block_stats", _p(self.X), F, blk, 1, count, _p(stats), _p(ws), st)
+                if self.world > 1:
+                    stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=True)
         scl = torch.empty(F, dtype=torch.float64, device=self.dev)
         _lib.call("omb_finalize_scale", _p(stats), F, count, SCALE_CODES[scale_type], _p(scl),
                   1 if axis_cnt is None else 0, _p(cnt), ncl, st)
@@ -147,11 +188,14 @@ class Engine:
     # ------------------------------------------------------------------------------------ K3
     def gram(self, centred=True, scaled=True):
         """G = X0^T X0 (m x m) from per-feature Grams of the centred rows."""
+        self._wait_arrival()
         F, ncl, m = self.F, self.n_c_loc, self.m
         st = _stream()
         Gf = torch.empty(F * m * m, dtype=torch.float64, device=self.dev)
         ws = _ws(_lib.load().omb_gram_ws_bytes(F, ncl, m), self.dev)
-        if centred and self._cnt_pending:               # row means + centred Grams from one read of X
+        if centred and getattr(self, "_Gf_cached", None) is not None:   # produced block by block behind the H2D copy
+            Gf, self._Gf_cached = self._Gf_cached, None
+        elif centred and self._cnt_pending:             # row means + centred Grams from one read of X
             _lib.call("omb_gram_rowmeans", _p(self.X), F, ncl, m, _p(self._cnt), _p(Gf), _p(ws), st)
             self._cnt_pending = False
         else:
@@ -187,6 +231,7 @@ class Engine:
     # ------------------------------------------------------------------------------------ K5
     def backproject(self, W, centred=True, scaled=True, norms=True):
         """Ut (r x ld, mode-major) = (X0 W)^T, plus the initial pivoted-QR norms."""
+        self._wait_arrival()
         W = W.contiguous()
         m, r = (int(v) for v in W.shape)
         assert m == self.m
@@ -395,6 +440,7 @@ class Engine:
 
     def scaled_matrix(self):
         """X0 = (X - cnt)/scl materialised on device (only when user code asks for .X0)."""
+        self._wait_arrival()
         X0 = torch.empty_like(self.X)
         _lib.call("omb_scale_rows", _p(self.X), self.F, self.n_c_loc, self.m, _p(self.cnt), _p(self.scl),
                   _p(X0), _stream())

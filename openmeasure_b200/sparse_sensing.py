@@ -153,8 +153,27 @@ class ROM:
                 X = np.ascontiguousarray(X, dtype=np.float64)
             dev = torch.device("cuda", torch.cuda.current_device())
             Xd = torch.empty(X.shape, dtype=torch.float64, device=dev)
-            Xd.copy_(torch.from_numpy(X), non_blocking=True)
-            self._eng = _eng.Engine(Xd, self.n_features, group=False)
+            Xh = torch.from_numpy(X)
+            F, n_c = self.n_features, X.shape[0] // self.n_features
+            if Xh.is_pinned() and F > 1:
+                # pinned host matrix: upload one feature block at a time on a copy stream; the engine's
+                # first stage consumes the blocks as they land (Engine.stats), so the statistics / Gram
+                # passes overlap the PCIe transfer instead of following it
+                copy_stream = torch.cuda.Stream(device=dev)
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))
+                arrival = []
+                with torch.cuda.stream(copy_stream):
+                    for f in range(F):
+                        Xd[f * n_c:(f + 1) * n_c].copy_(Xh[f * n_c:(f + 1) * n_c], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        arrival.append(ev)
+                Xd.record_stream(copy_stream)
+                self._eng = _eng.Engine(Xd, self.n_features, group=False)
+                self._eng._arrival = arrival
+            else:
+                Xd.copy_(Xh, non_blocking=True)
+                self._eng = _eng.Engine(Xd, self.n_features, group=False)
         return self._eng
 
     def _n_rows(self):
