@@ -35,6 +35,27 @@ constexpr int QR_NCAND = 4096;   // max CTAs of a pass kernel (argmax records)
 constexpr double QR_TOL3Z = 1.0536712127723509e-08;   // sqrt(2^-53), LAPACK tol3z
 constexpr int QR_LREG = 100;     // tallest trailing block of the register-resident (bit-exact) pass
 
+// Programmatic dependent launch: the kernels of the placement loop form a strict chain (pass -> panel
+// -> pass ...).  Each one lets its successor start launching at once (launch_dependents) and waits for
+// its predecessor's results at its own top (wait), so launch latency and CTA scheduling of kernel k+1
+// overlap the execution of kernel k instead of following its drain.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct Cand {
     double best;      // largest partial column norm (-1: none)
     double second;    // second largest (-1: none)
@@ -203,6 +224,7 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, 
 {
     __shared__ double s_q[QR_RMAX];
     __shared__ Cand s_c[GV_THREADS / 32];
+    pdl_enter();
     for (int k = threadIdx.x; k < L; k += GV_THREADS) s_q[k] = P->q[k];
     __syncthreads();
 
@@ -272,6 +294,7 @@ qr_apply1_kernel(const double* __restrict__ src, double* __restrict__ dst, int64
     __shared__ double s_v[LMAX];
     __shared__ double s_tau;
     __shared__ Cand s_c[AR_THREADS / 32];
+    pdl_enter();
     for (int k = threadIdx.x; k < LMAX; k += AR_THREADS) s_v[k] = (k < L) ? P->V[0][k] : 0.0;
     if (threadIdx.x == 0) s_tau = P->tau[0];
     __syncthreads();
@@ -364,6 +387,7 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
     __shared__ double sVt[8 * SVT];
     __shared__ double sT[8 * AM_ST];
     __shared__ Cand s_c[AM_THREADS / 32];
+    pdl_enter();
     for (int e = threadIdx.x; e < LP * 8; e += AM_THREADS) {
         const int k = e >> 3, a = e & 7;
         const double v = (k < L && a <= t) ? P->V[a][k] : 0.0;
@@ -671,6 +695,7 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
     __shared__ double s_z[QR_BMAX], s_g[QR_BMAX];
     __shared__ int64_t s_win[4];               // winner: global index, LAPACK key, local column, gap bits
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_enter();
 
     // 0. block state -> shared memory (independent of the pivot: overlaps the argmax reduction)
     for (int a = warp; a < t; a += PN_THREADS / 32)
@@ -989,7 +1014,7 @@ static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t 
             g = ntiles;
             if (g > (int64_t)sms * ar_min_blocks(lmax)) g = (int64_t)sms * ar_min_blocks(lmax);   // one wave
             if (g > QR_NCAND) g = QR_NCAND;
-            f1<<<(unsigned)g, AR_THREADS, 0, st>>>(src, d_work, n, r, i0, L, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+            launch_pdl(f1, dim3((unsigned)g), dim3(AR_THREADS), 0, st, src, d_work, n, r, i0, L, w.panel, w.vn1, w.vn2, s, sh, w.cand);
             if ((rc = check_launch("qr_apply1_kernel"))) return rc;
         } else {
             // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
@@ -1000,14 +1025,14 @@ static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t 
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fm, AM_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
             if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
             if (g > QR_NCAND) g = QR_NCAND;
-            fm<<<(unsigned)g, AM_THREADS, 0, st>>>(src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+            launch_pdl(fm, dim3((unsigned)g), dim3(AM_THREADS), 0, st, src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand);
             if ((rc = check_launch("qr_apply_mma_kernel"))) return rc;
         }
         *ncand = (int)g;
     } else {
         const int64_t gv = gemv_grid(n);
-        qr_gemv_kernel<<<(unsigned)gv, GV_THREADS, 0, st>>>(src, n, r, i0, L, t, (t + 1 == L) ? 1 : 0, w.panel, w.vn1,
-                                                           w.vn2, s, sh, w.cand);
+        launch_pdl(qr_gemv_kernel, dim3((unsigned)gv), dim3(GV_THREADS), 0, st, src, n, r, i0, L, t, (t + 1 == L) ? 1 : 0,
+                   (const Panel*)w.panel, w.vn1, w.vn2, s, sh, w.cand);
         if ((rc = check_launch("qr_gemv_kernel"))) return rc;
         *ncand = (int)gv;
     }
@@ -1047,9 +1072,9 @@ extern "C" int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, con
     int i0 = 0;
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        qr_panel_kernel<false><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, ncand, src, ri, i0, ri - i0, i, t,
-                                                          block == 1 ? 1 : 0, s, index_base, sh, nullptr, P2P{nullptr, nullptr, 0},
-                                                          w.vn1, d_piv, d_rdiag, d_gap);
+        launch_pdl(qr_panel_kernel<false>, dim3(1), dim3(PN_THREADS), 0, st, w.panel, (const Cand*)w.cand, ncand, src, ri, i0,
+                   ri - i0, i, t, block == 1 ? 1 : 0, s, index_base, sh, (const double*)nullptr, P2P{nullptr, nullptr, 0},
+                   w.vn1, d_piv, d_rdiag, d_gap);
         if ((rc = check_launch("qr_panel_kernel"))) return rc;
         if (i == (int)s - 1) break;           // no further pivot needed: skip the last pass
         if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
@@ -1152,8 +1177,8 @@ extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s,
     int i0 = 0;
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, i, t, 0, s, 0, sh,
-                                                         nullptr, pp, w.vn1, d_piv, d_rdiag, d_gap);
+        launch_pdl(qr_panel_kernel<true>, dim3(1), dim3(PN_THREADS), 0, st, w.panel, (const Cand*)w.cand, 0, src, ri, i0, ri - i0,
+                   i, t, 0, s, (int64_t)0, sh, (const double*)nullptr, pp, w.vn1, d_piv, d_rdiag, d_gap);
         if ((rc = check_launch("qr_panel_kernel"))) return rc;
         if (i == (int)s - 1) break;
         if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
