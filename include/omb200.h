@@ -98,6 +98,11 @@ int omb_gram_combine(const double* d_Gf, int64_t F, int64_t m, const double* d_s
  *      component i of eigenvector k, d_info (may be NULL) = sweeps used. */
 int omb_eigh_max_m(void);
 int omb_eigh_jacobi(const double* d_G, int64_t m, double* d_w, double* d_V, int* d_info, void* stream);
+/* sigma = sqrt(max(lambda, 0)) (m values) and W = V diag(1/sigma) (m x m, row-major like V) with a zero
+ * column for every sigma <= rel_floor * sigma_1: the weights of the back-projection U = X0 W[:, :r]
+ * (U[:, :r] of np.linalg.svd, sparse_sensing.py:272, :336). */
+int omb_pod_weights(const double* d_w, const double* d_V, int64_t m, double rel_floor, double* d_S, double* d_W,
+                    void* stream);
 
 /* ---- K5: back-projection U_r = X0 * W, W = V_r Sigma_r^-1 (m x r row-major), written mode-major,
  *      with the initial QRCP column norms vn[i] = ||U_r[i,:]||_2 fused (replaces U = Q*U_R inside

@@ -43,6 +43,7 @@ SIGNATURES = {
     "omb_p2p_allgather_buffer_doubles": (_i64, [_int, _i64]),
     "omb_p2p_allgather_error_index": (_i64, [_int, _i64]),
     "omb_p2p_allgather": (_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "omb_pod_weights": (_int, [_vp, _vp, _i64, C.c_double, _vp, _vp, _vp]),
     "omb_gem_ws_bytes": (_i64, []),
     "omb_gem_max_sensors": (_int, []),
     "omb_gem_variance": (_int, [_vp, _i64, _i64, _vp, _vp]),

@@ -267,6 +267,22 @@ eigh_jacobi_kernel(const double* __restrict__ G, int m, double* __restrict__ w_o
     if (threadIdx.x == 0 && info) *info = sweep;
 }
 
+// sigma = sqrt(max(lambda, 0)) and the back-projection weights W = V diag(1/sigma), with a zero weight
+// for modes whose singular value is numerically zero (row-centred data has rank m - 1): one launch
+// instead of a dozen framework element-wise kernels between the eigensolve and the back-projection.
+__global__ void __launch_bounds__(256)
+pod_weights_kernel(const double* __restrict__ w, const double* __restrict__ V, int m, double rel_floor,
+                   double* __restrict__ S, double* __restrict__ W)
+{
+    const double s0 = sqrt(fmax(w[0], 0.0));
+    for (int e = threadIdx.x; e < m * m; e += 256) {
+        const int q = e % m;
+        const double sq = sqrt(fmax(w[q], 0.0));
+        W[e] = (sq > s0 * rel_floor) ? V[e] * (1.0 / sq) : 0.0;
+        if (e < m) S[e] = sqrt(fmax(w[e], 0.0));
+    }
+}
+
 }  // namespace omb
 
 extern "C" int omb_eigh_max_m(void) { return omb::EJ_MAX; }
@@ -280,4 +296,14 @@ extern "C" int omb_eigh_jacobi(const double* d_G, int64_t m, double* d_w, double
     OMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eigh_jacobi_kernel<<<1, EJ_THREADS, smem, (cudaStream_t)stream>>>(d_G, (int)m, d_w, d_V, d_info);
     return check_launch("eigh_jacobi_kernel");
+}
+
+extern "C" int omb_pod_weights(const double* d_w, const double* d_V, int64_t m, double rel_floor, double* d_S, double* d_W,
+                               void* stream)
+{
+    using namespace omb;
+    OMB_CHECK_ARG(d_w && d_V && d_S && d_W, "null pointer");
+    OMB_CHECK_ARG(m >= 1 && m <= 4096, "m must be in [1, 4096]");
+    pod_weights_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_w, d_V, (int)m, rel_floor, d_S, d_W);
+    return check_launch("pod_weights_kernel");
 }

@@ -226,7 +226,12 @@ class Engine:
             # kernel is deterministic and its input G is bit-identical on every rank: no broadcast.)
             w = self.comm.bcast(w.contiguous(), 0)
             V = self.comm.bcast(V.contiguous(), 0)
-        return torch.sqrt(torch.clamp(w, min=0.0)), V
+        # sigma and the back-projection weights V diag(1/sigma) (zero for numerically-zero modes): one launch
+        S = torch.empty(m, dtype=torch.float64, device=self.dev)
+        Wfull = torch.empty(m, m, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_pod_weights", _p(w.contiguous()), _p(V.contiguous()), m, C.c_double(m * EPS), _p(S), _p(Wfull), _stream())
+        self.pod_weights = Wfull
+        return S, V
 
     # ------------------------------------------------------------------------------------ K5
     def backproject(self, W, centred=True, scaled=True, norms=True):

@@ -329,12 +329,9 @@ class ROM:
             S_h = S.cpu().numpy()
             lam = S_h ** 2
             r = self._choose_rank(100 * np.cumsum(lam) / np.sum(lam), eng.m, select_modes, n_modes)
-        Sr = S[:r]
         # modes whose singular value is numerically zero carry no information (row-centred data
-        # has rank m-1): back-project them with a zero weight instead of dividing by ~0
-        safe = Sr > S[0] * (eng.m * _eng.EPS)
-        W = torch.where(safe, 1.0 / torch.where(safe, Sr, torch.ones_like(Sr)), torch.zeros_like(Sr))
-        eng.backproject((V[:, :r] * W).contiguous(), centred=centred, scaled=scaled)
+        # has rank m-1): eig_pod's weights V diag(1/sigma) hold a zero column for them
+        eng.backproject(eng.pod_weights[:, :r].contiguous(), centred=centred, scaled=scaled)
         if S_h is None:
             S_h = S.cpu().numpy()
         S_h = S_h.copy()
