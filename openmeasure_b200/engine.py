@@ -210,9 +210,11 @@ class Engine:
         """m x m eigensolve -> singular values (descending) and right singular vectors (the
         largest-magnitude component of each vector positive)."""
         m = int(G.shape[0])
+        SV = None
         if m <= int(_lib.load().omb_eigh_max_m()):
             w = torch.empty(m, dtype=torch.float64, device=self.dev)
-            V = torch.empty(m, m, dtype=torch.float64, device=self.dev)
+            SV = torch.empty(m + m * m, dtype=torch.float64, device=self.dev)    # sigma | V: one D2H for the host side
+            V = SV[m:].view(m, m)
             _lib.call("omb_eigh_jacobi", _p(G.contiguous()), m, _p(w), _p(V), None, _stream())
         else:
             w, V = torch.linalg.eigh(G)
@@ -227,10 +229,14 @@ class Engine:
             w = self.comm.bcast(w.contiguous(), 0)
             V = self.comm.bcast(V.contiguous(), 0)
         # sigma and the back-projection weights V diag(1/sigma) (zero for numerically-zero modes): one launch
-        S = torch.empty(m, dtype=torch.float64, device=self.dev)
+        if SV is None:
+            SV = torch.empty(m + m * m, dtype=torch.float64, device=self.dev)
+            SV[m:].copy_(V.reshape(-1))
+            V = SV[m:].view(m, m)
+        S = SV[:m]
         Wfull = torch.empty(m, m, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_pod_weights", _p(w.contiguous()), _p(V.contiguous()), m, C.c_double(m * EPS), _p(S), _p(Wfull), _stream())
-        self.pod_weights = Wfull
+        _lib.call("omb_pod_weights", _p(w.contiguous()), _p(V), m, C.c_double(m * EPS), _p(S), _p(Wfull), _stream())
+        self.pod_weights, self.pod_sv = Wfull, SV
         return S, V
 
     # ------------------------------------------------------------------------------------ K5
@@ -315,9 +321,9 @@ class Engine:
         block = max(1, min(8, int(block)))
         work = torch.empty(self.ntiles, r, TB, dtype=torch.float64, device=self.dev)
         ws = _ws(_lib.load().omb_qrcp_ws_bytes(self.n_loc, r), self.dev)
-        piv = torch.empty(s, dtype=torch.int64, device=self.dev)
-        rdiag = torch.empty(s, dtype=torch.float64, device=self.dev)
-        gap = torch.empty(s, dtype=torch.float64, device=self.dev)
+        out = torch.empty(3 * s, dtype=torch.float64, device=self.dev)      # one buffer: one D2H for all three
+        piv, rdiag, gap = out[:s].view(torch.int64), out[s:2 * s], out[2 * s:]
+        self.qr_out = out
         if self.world == 1:
             _lib.call("omb_qrcp", _p(self.Ut), self.n_loc, r, s, _p(self.vn), _p(work), _p(ws),
                       block, 0, _p(piv), _p(rdiag), _p(gap), _stream())

@@ -332,10 +332,9 @@ class ROM:
         # modes whose singular value is numerically zero carry no information (row-centred data
         # has rank m-1): eig_pod's weights V diag(1/sigma) hold a zero column for them
         eng.backproject(eng.pod_weights[:, :r].contiguous(), centred=centred, scaled=scaled)
-        if S_h is None:
-            S_h = S.cpu().numpy()
-        S_h = S_h.copy()
-        Vr_h = V[:, :r].cpu().numpy()
+        sv_h = eng.pod_sv.cpu().numpy()                       # sigma | V in one D2H
+        S_h = sv_h[:eng.m].copy()
+        Vr_h = sv_h[eng.m:].reshape(eng.m, eng.m)[:, :r].copy()
         # smallest retained singular value that carries information (the numerically-zero mode of
         # row-centred data, back-projected with a zero weight, is excluded from the accuracy estimate)
         live = S_h[:r][S_h[:r] > S_h[0] * (eng.m * _eng.EPS)]
@@ -486,10 +485,12 @@ class SPR(ROM):
             eng.mask_rows(torch.from_numpy(np.asarray(mask, dtype=bool)).to(eng.dev))
             self._host.pop("Ur", None)
         piv, rdiag, gap = eng.qrcp(block=block)
-        self.qr_pivots = piv.cpu().numpy()
+        out = eng.qr_out.cpu()                            # pivots | R diagonal | gaps in one D2H
+        s_ = int(piv.numel())
+        self.qr_pivots = out[:s_].view(torch.int64).numpy().copy()
         eng.check_p2p()
-        self.qr_rdiag = rdiag.cpu().numpy()
-        self.qr_gap = gap.cpu().numpy()
+        self.qr_rdiag = out[s_:2 * s_].numpy().copy()
+        self.qr_gap = out[2 * s_:].numpy().copy()
         return SensorMatrix(self.qr_pivots, self._n_rows())
 
     # ------------------------------------------------------------------ train (a8)
