@@ -79,7 +79,16 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1 to its children, so the limit is
+    # lifted before numpy / scipy (OpenBLAS) are first imported, and again through threadpoolctl
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(os.cpu_count() or 1)
     import numpy as np  # noqa: F401
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     frac = 0.25
     X, n_c = cpu_sample(w, frac)
     for _ in range(min(args.warmup, 1)):
