@@ -393,7 +393,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": x_bytes_glob / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(8 * n_loc * m * world),
-               "d2h_bytes_per_step": int((3 * r * 8 + m * 8 + m * r * 8) * world), "ms_per_step": dt * 1e3,
+               "d2h_bytes_per_step": int((3 * r * 8 + (m + m * m) * 8) * world),   # pivots|rdiag|gaps + sigma|V "ms_per_step": dt * 1e3,
                "api": "SPR(X_host, F, xyz).fit(select_modes='number', n_modes=r); optimal_placement()"}
         del Xh_t
 
