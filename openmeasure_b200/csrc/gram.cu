@@ -255,10 +255,21 @@ static GramPlan gram_big_plan(int64_t F, int64_t n_c, int64_t m)
     GramPlan p;
     p.T = (int)ceil_div(m, GB_T);
     p.ntiles = p.T * (p.T + 1) / 2;
-    // one CTA per SM (shared memory): aim at one full wave, or whole waves when the tiles alone exceed it
-    int64_t splits = (int64_t)sm_count() / ((int64_t)F * p.ntiles);
-    if (splits < 1) splits = 1;
+    // one CTA per SM (shared memory).  Few tiles: one full wave.  More tile CTAs than SMs: split the rows
+    // so that the last wave is (nearly) full -- time ~ ceil(tiles * s / SMs) / s -- e.g. m = 1024, F = 9:
+    // 324 tile CTAs = 2.19 waves would cost 3; 5 row splits give 11 waves of a fifth = 2.2
+    const int64_t sms = sm_count(), tiles = (int64_t)F * p.ntiles;
     int64_t max_splits = ceil_div(n_c, 8 * GB_K);
+    if (max_splits < 1) max_splits = 1;
+    int64_t splits = sms / tiles;
+    if (splits < 1) {
+        double best = 1e30;
+        splits = 1;
+        for (int64_t sp = 1; sp <= 16 && sp <= max_splits; ++sp) {
+            const double cost = (double)ceil_div(tiles * sp, sms) / (double)sp;
+            if (cost < best * 0.97) { best = cost; splits = sp; }
+        }
+    }
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.rows_per_split = round_up(ceil_div(n_c, splits), GB_K);
