@@ -286,10 +286,12 @@ static bool gram_big_ok(const double* X, int64_t m)
 // Few-snapshot variant (m <= 64): the whole m x m Gram fits one warp's accumulators, so every
 // warp sweeps its own rows and keeps the NB(NB+1)/2 upper-triangular 8 x 8 blocks (NB = ceil(m/8))
 // in registers.  A fragment X[k0 + lane%4][8b + lane/4] serves as both operands of the symmetric
-// product, and is loaded straight from global memory (four 64-byte row segments per load; a row's
-// 8m bytes stay in L1 across its NB loads): X makes one trip from HBM, no staging, no barriers.
+// product.  A producer warp streams chunks of 4 * GS_WARPS rows through a 4-stage shared-memory ring
+// with bulk (TMA) copies and mbarriers; consumer warp w takes rows 4w .. 4w+3 of every chunk, and
+// -- when asked -- derives np.average(x, axis=1) of those rows from the same fragments (bit-exact:
+// the fragment layout is numpy's accumulator layout).  X makes one trip from HBM for both results.
 // Warps are combined in a fixed order through shared memory; the CTA's partial goes out in the
-// 64 x 64 tile format of the general kernel and is reduced by the same fixed-order pass.
+// 64 x 64 tile format of the staged kernel and is reduced by the same fixed-order pass.
 // ---------------------------------------------------------------------------------------------
 constexpr int GS_WARPS = 15;                      // consumer warps: warp w owns k-step w of every chunk
 constexpr int GS_THREADS = (GS_WARPS + 1) * 32;   // + one producer warp driving the TMA ring

@@ -4,10 +4,12 @@
 // blocks (reference sparse_sensing.py:110-161).  numpy reduces a contiguous FP64 range with a
 // fixed tree: ranges > 128 elements split at n2 = (n/2) & ~7, leaves (<= 128 elements) are summed
 // with 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail.
-// The kernels evaluate exactly that tree: one 8-lane group owns one leaf (lane k = accumulator k,
-// a 64-byte coalesced read per step), leaves are combined up the tree in shared memory and then in
-// a small global up-sweep.  Nodes that do not exist at a given depth are tracked with a flag, not
-// with +0.0, so even the sign of zero follows numpy.
+// The kernels evaluate exactly that tree: a quad of lanes owns one leaf (lane q = accumulators 2q and
+// 2q+1, one 128-bit load per octet, all loads of a leaf issued before its first add), a warp owns
+// the 8 leaves of a depth-(D-3) node and combines them by shuffles, and a small second kernel sweeps
+// the levels above.  Nodes that do not exist at a given depth are tracked with a flag, not with
+// +0.0, so even the sign of zero follows numpy.  (Row means of m <= 64 snapshots come from the Gram
+// kernel's fragments instead, gram.cu; the 8-lane row kernel below serves m > 1024.)
 #include "common.cuh"
 #include "../../include/omb200.h"
 
