@@ -29,10 +29,28 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """nvcc every translation unit for sm_100a (in parallel: no device symbol crosses a file) and link
+    libomb200.so in-tree."""
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    subprocess.check_call(cmd)
+    import concurrent.futures
+    import tempfile
+    cflags = [f for f in FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else [])
+    with tempfile.TemporaryDirectory(prefix="omb200_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+            out = subprocess.run([NVCC] + cflags + ["-c", "-o", obj, src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                 text=True)
+            return obj, out.returncode, out.stdout
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            results = list(pool.map(compile_one, sources()))
+        for obj, rc, log in results:
+            if verbose or rc:
+                print(log, end="")
+            if rc:
+                raise subprocess.CalledProcessError(rc, "nvcc -c " + obj)
+        subprocess.check_call([NVCC, "--shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-o", LIB] + [obj for obj, _, _ in results])
     return LIB
 
 
