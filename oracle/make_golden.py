@@ -98,14 +98,31 @@ def _gem_case(sps, name, X, F, n_modes, n_sensors, d_min, seed, rng):
     print(f"{name}: n={n} r={spr.r} gem sensors={piv} -> {os.path.getsize(path)/1e3:.0f} kB")
 
 
+def _scaling_case(sps, name, rng):
+    """ROM.scale_data of the unmodified reference for EVERY scaling type it implements
+    (sparse_sensing.py:114-161), both centring modes: X_cnt, X_scl and X0 on one small matrix."""
+    F, n_c, m = 3, 150, 11
+    X = rng.random((F * n_c, m)) * 10.0 ** rng.integers(-1, 3, (F * n_c, 1)) + 0.5
+    out = dict(X=X, F=np.int64(F))
+    for st in ("std", "none", "pareto", "vast", "range", "level", "max", "variance", "median", "poisson", "l2-norm"):
+        for ax, tag in ((1, "row"), (None, "blk")):
+            rom = sps.ROM(X.copy(), F, None)
+            X0 = rom.scale_data(st, ax)
+            key = st.replace("-", "_") + "_" + tag
+            out[key + "_cnt"], out[key + "_scl"], out[key + "_X0"] = rom.X_cnt, rom.X_scl, X0
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {len(out) - 2} arrays -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
 def main():
     sps = _import_reference()
     sys.path.insert(0, ROOT)
     from oracle import synth
     os.makedirs(GOLD, exist_ok=True)
     rng = np.random.default_rng(20261018)
-    gem_only = "--gem-only" in sys.argv         # leaves the committed g1..g5 fixtures untouched
-    if not gem_only:
+    partial = ("--gem-only" in sys.argv) or ("--scaling" in sys.argv)   # leave the g1..g5 fixtures untouched
+    if not partial:
 
         # g1: the reference unit tests' own shape (tests/test_rom.py:8-13: 2 features x 10 points x 5)
         _case(sps, "g1_unit_20x5", rng.random((20, 5)), 2, 4, rng=rng)
@@ -119,6 +136,11 @@ def main():
               scale_type="range", axis_cnt=None, sigma=0.02, rng=rng)
         # g5: wider snapshot set, m > 128 exercises the multi-leaf row-mean tree: 2 x 300 x 160, r = 20
         _case(sps, "g5_synth_600x160_r20", synth.snapshots(2, 300, 160, 20), 2, 20, rng=rng)
+    # s1: every scaling type x both centring modes (never overwritten unless --scaling is given)
+    if "--scaling" in sys.argv or not os.path.exists(os.path.join(GOLD, "s1_scalings_450x11.npz")):
+        _scaling_case(sps, "s1_scalings_450x11", np.random.default_rng(99))
+    if "--scaling" in sys.argv:
+        return
     # g6/g7: GEM placement (sparse_sensing.py:586-698) with a user mask, without / with a d_min radius
     rng2 = np.random.default_rng(7)
     _gem_case(sps, "g6_gem_900x20_r8", synth.snapshots(3, 300, 20, 8), 3, 8, 6, 0.0, 11, rng2)

@@ -19,7 +19,7 @@ def pytest_configure(config):
 def golden_names(gem=False):
     """Pipeline fixtures (g1..g5) or, with gem=True, the GEM placement fixtures (g6, g7)."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if ("_gem_" in n) == gem]
+    return [n for n in names if n.startswith("g") and ("_gem_" in n) == gem]
 
 
 def load_golden(name):

@@ -150,3 +150,19 @@ def test_gem_oracle_matches_reference_golden(golden_gem):
         P = np.tile(g["xyz"], (int(g["F"]), 1))[sensors]
         D = np.linalg.norm(P[:, None, :] - P[None, :, :], axis=2)
         assert np.all(D[np.triu_indices(len(sensors), 1)] >= float(g["d_min"]))
+
+
+# ---- every scaling type x both centring modes: oracle == unmodified reference, bit for bit -------
+SCALINGS = ("std", "none", "pareto", "vast", "range", "level", "max", "variance", "median", "poisson", "l2-norm")
+
+
+@pytest.mark.parametrize("scale_type", SCALINGS)
+@pytest.mark.parametrize("axis_cnt,tag", [(1, "row"), (None, "blk")])
+def test_oracle_scalings_match_reference_golden(scale_type, axis_cnt, tag):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "s1_scalings_450x11.npz"))
+    X0, cnt, scl = po.center_scale(z["X"], int(z["F"]), scale_type, axis_cnt)
+    key = scale_type.replace("-", "_") + "_" + tag
+    np.testing.assert_array_equal(cnt, z[key + "_cnt"])
+    np.testing.assert_array_equal(scl, z[key + "_scl"])
+    np.testing.assert_array_equal(X0, z[key + "_X0"])
