@@ -694,3 +694,25 @@ def test_batched_reconstruct_matches_numpy(torch_cuda, n_c, r, N):
     scl = np.repeat(eng.scl.cpu().numpy(), n_c)[:, None]
     ref = scl * (Ur @ A.T) + eng.cnt.cpu().numpy()[:, None]
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# every scaling type x both centring modes against the reference's own outputs (fixture s1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scale_type", ["std", "none", "pareto", "vast", "range", "level", "max", "variance",
+                                        "median", "poisson", "l2-norm"])
+@pytest.mark.parametrize("axis_cnt,tag", [(1, "row"), (None, "blk")])
+def test_all_scalings_match_reference_golden(torch_cuda, scale_type, axis_cnt, tag):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "s1_scalings_450x11.npz"))
+    rom = _sps().ROM(z["X"], int(z["F"]), None)
+    X0 = rom.scale_data(scale_type, axis_cnt)
+    key = scale_type.replace("-", "_") + "_" + tag
+    np.testing.assert_array_equal(rom.X_cnt, z[key + "_cnt"])
+    if scale_type in ("vast", "l2-norm"):
+        # derived from two tree sums (sd^2 / mean; sqrt(q + N mean^2)): within 2 ulp of numpy's own route
+        np.testing.assert_allclose(rom.X_scl, z[key + "_scl"], rtol=4e-16)
+        np.testing.assert_allclose(X0, z[key + "_X0"], rtol=1e-14, atol=1e-14)
+    else:
+        np.testing.assert_array_equal(rom.X_scl, z[key + "_scl"])
+        np.testing.assert_array_equal(X0, z[key + "_X0"])
