@@ -115,13 +115,51 @@ def _scaling_case(sps, name, rng):
     print(f"{name}: {len(out) - 2} arrays -> {os.path.getsize(path)/1e3:.0f} kB")
 
 
+def _extras_case(sps, name, rng):
+    """The API corners around the path, from the unmodified reference: fit(basis=...), train with a general
+    (non one-hot) dense C and cond=True (:797, :813-820), weighted predict (:871-878), reconstruct and
+    unscale_data with a sampling matrix (:365-368, :233)."""
+    from oracle import synth
+    F, n_c, m, r = 3, 300, 20, 8
+    X = synth.snapshots(F, n_c, m, r)
+    n = F * n_c
+    spr = sps.SPR(X.copy(), F, np.zeros((n_c, 3)))
+    spr.fit(select_modes="number", n_modes=r)
+    Ur, Ar_fit = spr.Ur.copy(), spr.Ar.copy()
+    s = 12
+    C = np.zeros((s, n))
+    for i in range(s):                                   # line-of-sight-like rows: a few cells of one feature
+        f = i % F
+        cols = f * n_c + rng.choice(n_c, 5, replace=False)
+        C[i, cols] = rng.random(5)
+    spr.train(C, cond=True)
+    ys = []
+    for t in range(3):
+        x = X[:, t] * (1.0 + 0.01 * rng.standard_normal(n))
+        y = np.zeros((s, 3))
+        y[:, 0] = C @ x
+        y[:, 1] = 0.02 * np.abs(y[:, 0]) + 1e-3
+        y[:, 2] = np.arange(s) % F
+        ys.append(y)
+    Ar_p, Ar_sig = spr.predict(ys)
+    S = rng.random((9, n)) * (rng.random((9, n)) < 0.02)
+    Xs = spr.reconstruct(Ar_p, sampling=S)
+    x0 = rng.standard_normal(9)
+    xs = spr.unscale_data(x0, sampling=S)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, X=X, F=np.int64(F), r=np.int64(r), Ur=Ur, Ar=Ar_fit, C=C, Theta=spr.Theta, k=np.float64(spr.k),
+                        Y=np.stack(ys), Ar_pred=Ar_p, Ar_sigma=Ar_sig, S=S, X_rec_s=Xs, x0=x0, x_uns=xs,
+                        cnt_vector=spr.cnt_vector, scl_vector=spr.scl_vector)
+    print(f"{name}: k={spr.k:.3f} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
 def main():
     sps = _import_reference()
     sys.path.insert(0, ROOT)
     from oracle import synth
     os.makedirs(GOLD, exist_ok=True)
     rng = np.random.default_rng(20261018)
-    partial = ("--gem-only" in sys.argv) or ("--scaling" in sys.argv)   # leave the g1..g5 fixtures untouched
+    partial = bool({"--gem-only", "--scaling", "--extras"} & set(sys.argv))   # leave the g1..g5 fixtures untouched
     if not partial:
 
         # g1: the reference unit tests' own shape (tests/test_rom.py:8-13: 2 features x 10 points x 5)
@@ -140,6 +178,11 @@ def main():
     if "--scaling" in sys.argv or not os.path.exists(os.path.join(GOLD, "s1_scalings_450x11.npz")):
         _scaling_case(sps, "s1_scalings_450x11", np.random.default_rng(99))
     if "--scaling" in sys.argv:
+        return
+    # x1: general C + cond, weighted predict, sampling matrices
+    if "--extras" in sys.argv or not os.path.exists(os.path.join(GOLD, "x1_extras_900x20_r8.npz")):
+        _extras_case(sps, "x1_extras_900x20_r8", np.random.default_rng(5))
+    if "--extras" in sys.argv:
         return
     # g6/g7: GEM placement (sparse_sensing.py:586-698) with a user mask, without / with a d_min radius
     rng2 = np.random.default_rng(7)

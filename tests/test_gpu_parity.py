@@ -716,3 +716,26 @@ def test_all_scalings_match_reference_golden(torch_cuda, scale_type, axis_cnt, t
     else:
         np.testing.assert_array_equal(rom.X_scl, z[key + "_scl"])
         np.testing.assert_array_equal(X0, z[key + "_X0"])
+
+
+# ---------------------------------------------------------------------------------------------
+# API corners against the reference's own outputs (fixture x1): fit(basis=...), train with a general
+# dense C and cond=True, weighted predict, reconstruct / unscale_data with a sampling matrix
+# ---------------------------------------------------------------------------------------------
+def test_api_extras_match_reference_golden(torch_cuda):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "x1_extras_900x20_r8.npz"))
+    F, r = int(z["F"]), int(z["r"])
+    n_c = z["X"].shape[0] // F
+    spr = _sps().SPR(z["X"], F, np.zeros((n_c, 3)))
+    spr.fit(select_modes="number", n_modes=r, basis=(z["Ur"], z["Ar"]))     # the reference's own basis (signs)
+    spr.train(z["C"], cond=True)
+    np.testing.assert_allclose(spr.Theta, z["Theta"], rtol=1e-12, atol=1e-14)
+    assert abs(spr.k - float(z["k"])) / float(z["k"]) < 1e-10
+    Ar_p, Ar_sig = spr.predict(list(z["Y"]))
+    np.testing.assert_allclose(Ar_p, z["Ar_pred"], rtol=1e-9, atol=1e-10 * np.abs(z["Ar_pred"]).max())
+    np.testing.assert_allclose(Ar_sig, z["Ar_sigma"], rtol=1e-9, atol=1e-10 * np.abs(z["Ar_sigma"]).max())
+    np.testing.assert_allclose(spr.cnt_vector, z["cnt_vector"], rtol=1e-13)
+    np.testing.assert_array_equal(spr.scl_vector, z["scl_vector"])
+    np.testing.assert_allclose(spr.reconstruct(Ar_p, sampling=z["S"]), z["X_rec_s"], rtol=1e-10)
+    np.testing.assert_allclose(spr.unscale_data(z["x0"], sampling=z["S"]), z["x_uns"], rtol=1e-13)
