@@ -44,6 +44,13 @@ enum {
     OMB_SCALE_POISSON = 8, OMB_SCALE_L2NORM = 9
 };
 
+/* ---- measured FP64 tensor-pipe peak (no reference counterpart; bench.py's roofline denominator) --
+ * Runs a register-only DMMA.8x8x4 stream for about ms_target milliseconds on every SM (synchronous:
+ * returns after the kernel) and reports TFLOP/s and the measured duration.  d_scratch: at least
+ * 2 * SMs * 256 doubles.  ~5 ms = burst figure, >= 300 ms = sustained under the power cap. */
+int omb_fp64_peak(double ms_target, double* d_scratch, int64_t scratch_doubles, double* h_tflops,
+                  double* h_ms, void* stream);
+
 /* ---- synthetic snapshots (no reference counterpart; DESIGN.md "Synthetic workload") -------- */
 int64_t omb_synth_ws_bytes(int64_t F, int64_t m, int64_t K);
 int omb_synth_fill(double* d_X, int64_t F, int64_t n_cells, int64_t cell0, int64_t ncell_loc,
@@ -167,6 +174,12 @@ int64_t omb_p2p_allgather_buffer_doubles(int world, int64_t capacity);
 int64_t omb_p2p_allgather_error_index(int world, int64_t capacity);
 int omb_p2p_allgather(const double* d_src, int64_t n, double* d_out, const void* d_peers, double* d_mine,
                       int64_t capacity, int64_t seq, int rank, int world, void* stream);
+/* All-reduce over the same buffers (shares the seq counter with omb_p2p_allgather): d_out[k] = the n
+ * payload elements of all ranks combined IN RANK ORDER (identical bits on every rank).
+ *   op 0: sum; op 1: groups of 4 = block statistics {sum, min, max, rank 0's}; op 2: element 3 of every
+ *   group summed (np.std's second pass), the others rank 0's value (sparse_sensing.py:112-161 across ranks) */
+int omb_p2p_allreduce(const double* d_src, int64_t n, double* d_out, const void* d_peers, double* d_mine,
+                      int64_t capacity, int64_t seq, int rank, int world, int op, void* stream);
 
 /* ---- GEM: greedy entropy-maximisation placement (SPR.gem, sparse_sensing.py:586-698; reached via
  *      optimal_placement(calc_type='gem') :745-751).  One streaming pass over the basis per sensor.

@@ -14,6 +14,7 @@ SIGNATURES = {
     "omb_last_error": (C.c_char_p, []),
     "omb_launch_count": (_i64, []),
     "omb_launch_count_reset": (None, []),
+    "omb_fp64_peak": (_int, [_dbl, _vp, _i64, _vp, _vp, _vp]),
     "omb_synth_ws_bytes": (_i64, [_i64, _i64, _i64]),
     "omb_synth_fill": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _vp, _vp, _dbl, _vp, _vp]),
     "omb_row_means": (_int, [_vp, _i64, _i64, _vp, _vp]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "omb_p2p_allgather_buffer_doubles": (_i64, [_int, _i64]),
     "omb_p2p_allgather_error_index": (_i64, [_int, _i64]),
     "omb_p2p_allgather": (_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "omb_p2p_allreduce": (_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp]),
     "omb_pod_weights": (_int, [_vp, _vp, _i64, C.c_double, _vp, _vp, _vp]),
     "omb_gem_ws_bytes": (_i64, []),
     "omb_gem_max_sensors": (_int, []),

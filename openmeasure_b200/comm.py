@@ -26,6 +26,22 @@ class SingleComm:
     def bcast(self, t, src=0):
         return t
 
+    def check(self):
+        pass
+
+    def combine_stats(self, stats, F, sq):
+        """Block statistics (F*4: sum, min, max, sqdev per feature) combined over the ranks in rank
+        order -- identical bits on every rank."""
+        if self.world == 1:
+            return stats
+        return combine_block_stats(self.allgather(stats), F, sq)
+
+    def sum_ordered(self, t):
+        """Element-wise sum of t over the ranks, added in rank order (identical bits on every rank)."""
+        if self.world == 1:
+            return t
+        return ordered_sum(self.allgather(t)).view_as(t)
+
 
 class TorchDistComm(SingleComm):
     def __init__(self, group=None):
@@ -35,26 +51,67 @@ class TorchDistComm(SingleComm):
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
-    P2P_CAPACITY = 8192          # doubles per rank and call served by the peer-memory all-gather
+    P2P_CAPACITY = 8192          # doubles per rank and call served by the peer-memory collectives
+
+    def _p2p(self, flat):
+        """Peer-memory state when `flat` qualifies for the one-kernel collectives, else None."""
+        if flat.is_cuda and flat.dtype == torch.float64 and 0 < flat.numel() <= self.P2P_CAPACITY:
+            return p2p_coll_state(self, flat.device, self.P2P_CAPACITY)
+        return None
+
+    def _p2p_launch(self, name, st, flat, out, *extra):
+        import ctypes as C
+        from . import _lib
+        st["seq"] += 1
+        _lib.call(name, C.c_void_p(flat.data_ptr()), flat.numel(), C.c_void_p(out.data_ptr()),
+                  C.c_void_p(st["peers_dev"]), C.c_void_p(st["buf"].data_ptr()), self.P2P_CAPACITY,
+                  st["seq"], self.rank, self.world, *extra, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self.p2p_collectives = getattr(self, "p2p_collectives", 0) + 1
+        self._p2p_used = st
 
     def allgather(self, t):
         flat = t.contiguous().reshape(-1)
         out = torch.empty(self.world * flat.numel(), dtype=flat.dtype, device=flat.device)
-        if flat.is_cuda and flat.dtype == torch.float64 and 0 < flat.numel() <= self.P2P_CAPACITY:
-            st = p2p_coll_state(self, flat.device, self.P2P_CAPACITY)
-            if st is not None:
-                # small FP64 payload: one kernel stores it into every peer's symmetric buffer (tagged
-                # low-latency words) and polls its own -- a few microseconds instead of an NCCL launch
-                import ctypes as C
-                from . import _lib
-                st["seq"] += 1
-                _lib.call("omb_p2p_allgather", C.c_void_p(flat.data_ptr()), flat.numel(), C.c_void_p(out.data_ptr()),
-                          C.c_void_p(st["peers_dev"]), C.c_void_p(st["buf"].data_ptr()), self.P2P_CAPACITY,
-                          st["seq"], self.rank, self.world, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-                self.p2p_collectives = getattr(self, "p2p_collectives", 0) + 1
-                return out.view(self.world, flat.numel())
+        st = self._p2p(flat)
+        if st is not None:
+            # small FP64 payload: one kernel stores it into every peer's symmetric buffer (tagged
+            # low-latency words) and polls its own -- a few microseconds instead of an NCCL launch
+            self._p2p_launch("omb_p2p_allgather", st, flat, out)
+            return out.view(self.world, flat.numel())
         self.dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.view(self.world, flat.numel())
+
+    def _allreduce(self, t, op):
+        flat = t.contiguous().reshape(-1)
+        st = self._p2p(flat)
+        if st is None:
+            return None
+        out = torch.empty_like(flat)
+        self._p2p_launch("omb_p2p_allreduce", st, flat, out, op)      # exchange + rank-ordered combine: one kernel
+        return out
+
+    def combine_stats(self, stats, F, sq):
+        out = self._allreduce(stats, 2 if sq else 1)
+        return out if out is not None else combine_block_stats(self.allgather(stats), F, sq)
+
+    def sum_ordered(self, t):
+        out = self._allreduce(t, 0)
+        return out.view_as(t) if out is not None else ordered_sum(self.allgather(t)).view_as(t)
+
+    def check(self):
+        """Raise if a peer never published during a peer-memory collective since the last check (the
+        kernels give up after 10 s and set an error word; the payload they returned is then garbage).
+        Host-synchronising: call it where the host waits for results anyway."""
+        st = getattr(self, "_p2p_used", None)
+        if st is None:
+            return
+        from . import _lib
+        idx = int(_lib.load().omb_p2p_allgather_error_index(self.world, self.P2P_CAPACITY))
+        word = st["buf"][idx:idx + 1].view(torch.int64)
+        if int(word.item()) != 0:
+            word.zero_()
+            raise _lib.OmbError("peer-memory collective: a peer rank did not publish its payload (10 s timeout); "
+                                "statistics / Gram / sensor rows of this step are invalid")
 
     def bcast(self, t, src=0):
         gsrc = src if self.group is None else self.dist.get_global_rank(self.group, src)
@@ -63,6 +120,28 @@ class TorchDistComm(SingleComm):
 
 
 _P2P_CACHE = {}
+
+
+def _one_rank_per_gpu(comm):
+    """The peer-memory kernels spin on words another rank's kernel writes: every rank's kernel must be
+    resident at the same time, i.e. every rank needs a GPU of its own (two ranks sharing one GPU would
+    wait on each other until the time-out).  Raises -> the caller falls back to NCCL."""
+    if comm.world > torch.cuda.device_count() and not _all_ranks_distinct_devices(comm):
+        raise RuntimeError("world size %d exceeds the %d visible GPUs: ranks would share a GPU"
+                           % (comm.world, torch.cuda.device_count()))
+
+
+def _all_ranks_distinct_devices(comm):
+    """Multi-node or masked-visibility layouts: accept when every rank of this host reports a distinct
+    device UUID."""
+    try:
+        uuid = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+        mine = torch.tensor([hash(uuid) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+        allv = torch.empty(comm.world, dtype=torch.int64, device="cuda")
+        comm.dist.all_gather_into_tensor(allv, mine, group=comm.group)
+        return len(set(allv.tolist())) == comm.world
+    except Exception:
+        return False
 
 
 def p2p_state(comm, device, ndoubles):
@@ -76,6 +155,7 @@ def p2p_state(comm, device, ndoubles):
     st = _P2P_CACHE.get(key)
     if st is None or st["buf"].numel() < ndoubles:
         try:
+            _one_rank_per_gpu(comm)
             import torch.distributed._symmetric_memory as symm_mem
             grp = comm.group if comm.group is not None else comm.dist.group.WORLD
             buf = symm_mem.empty(int(ndoubles), dtype=torch.float64, device=device)
@@ -104,6 +184,7 @@ def p2p_coll_state(comm, device, capacity):
     st = _P2P_COLL_CACHE.get(key)
     if st is None:
         try:
+            _one_rank_per_gpu(comm)
             import torch.distributed._symmetric_memory as symm_mem
             from . import _lib
             nd = int(_lib.load().omb_p2p_allgather_buffer_doubles(comm.world, int(capacity)))

@@ -88,10 +88,15 @@ class Engine:
         self.ntiles = tiles_for(self.n_loc)
 
     def check_p2p(self):
-        """Raise if a peer never answered during the last peer-memory placement."""
+        """Raise if a peer never answered during a peer-memory exchange since the last check (the pivot
+        exchange of the placement, the small collectives of the fit).  Synchronises with the device."""
+        self.comm.check()
         st = getattr(self, "_p2p_err", None)
-        if st is not None and st[0][st[1]:st[1] + 1].view(torch.int64).item() != 0:
-            raise _lib.OmbError("multi-rank placement: a peer rank did not publish its record (10 s timeout)")
+        if st is not None:
+            word = st[0][st[1]:st[1] + 1].view(torch.int64)
+            if word.item() != 0:
+                word.zero_()
+                raise _lib.OmbError("multi-rank placement: a peer rank did not publish its record (10 s timeout)")
 
     @property
     def cnt(self):
@@ -134,10 +139,12 @@ class Engine:
         count = self.n_c * m
         self._Gf_cached = None
         arrival = getattr(self, "_arrival", None)
-        if arrival is not None and self.world == 1:
-            # X is still on its way from the host, one feature block at a time (ROM._engine): run every
-            # pass of this stage on a block as soon as it has landed -- the statistics and, when the
-            # caller defers the row means, the Gram pass hide behind the PCIe copy of the next blocks
+        if arrival is not None:
+            # X is still on its way from the host, one feature block at a time (ROM._engine / from_host):
+            # run every pass of this stage on a block as soon as it has landed -- the statistics and, when
+            # the caller defers the row means, the Gram pass hide behind the PCIe copy of the next blocks.
+            # Multi-rank: the second-moment pass needs the GLOBAL block sums, so it runs over the whole
+            # shard after the first exchange (the Gram, the bulk of the work, still overlaps the upload).
             self._arrival = None
             L = _lib.load()
             ws1 = _ws(L.omb_block_stats_ws_bytes(1, blk), self.dev)
@@ -150,7 +157,7 @@ class Engine:
                 cur.wait_event(arrival[f])
                 Xf, sf, cf = self.X[f * ncl:(f + 1) * ncl], stats[4 * f:4 * f + 4], cnt[f * ncl:(f + 1) * ncl]
                 _lib.call("omb_block_stats", _p(Xf), 1, blk, 0, count, _p(sf), _p(ws1), st)
-                if scale_type in NEEDS_SQDEV:
+                if scale_type in NEEDS_SQDEV and self.world == 1:
                     _lib.call("omb_block_stats", _p(Xf), 1, blk, 1, count, _p(sf), _p(ws1), st)
                 if fuse_gram:
                     _lib.call("omb_gram_rowmeans", _p(Xf), 1, ncl, m, _p(cf), _p(Gf[f * m * m:(f + 1) * m * m]), _p(gws), st)
@@ -158,11 +165,12 @@ class Engine:
                     _lib.call("omb_row_means", _p(Xf), ncl, m, _p(cf), st)
             if fuse_gram:
                 self._Gf_cached = Gf
+            if self.world > 1:
+                stats = self.comm.combine_stats(stats, F, sq=False)
+                if scale_type in NEEDS_SQDEV:
+                    _lib.call("omb_block_stats", _p(self.X), F, blk, 1, count, _p(stats), _p(ws), st)
+                    stats = self.comm.combine_stats(stats, F, sq=True)
         else:
-            if arrival is not None:                         # multi-rank: wait for the whole shard
-                for ev in arrival:
-                    torch.cuda.current_stream().wait_event(ev)
-                self._arrival = None
             if axis_cnt == 1:
                 if defer_row_means:
                     pending = True
@@ -170,11 +178,11 @@ class Engine:
                     _lib.call("omb_row_means", _p(self.X), self.n_loc, m, _p(cnt), st)
             _lib.call("omb_block_stats", _p(self.X), F, blk, 0, count, _p(stats), _p(ws), st)
             if self.world > 1:
-                stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=False)
+                stats = self.comm.combine_stats(stats, F, sq=False)
             if scale_type in NEEDS_SQDEV:
                 _lib.call("omb_block_stats", _p(self.X), F, blk, 1, count, _p(stats), _p(ws), st)
                 if self.world > 1:
-                    stats = _comm.combine_block_stats(self.comm.allgather(stats), F, sq=True)
+                    stats = self.comm.combine_stats(stats, F, sq=True)
         scl = torch.empty(F, dtype=torch.float64, device=self.dev)
         _lib.call("omb_finalize_scale", _p(stats), F, count, SCALE_CODES[scale_type], _p(scl),
                   1 if axis_cnt is None else 0, _p(cnt), ncl, st)
@@ -203,7 +211,7 @@ class Engine:
         G = torch.empty(m, m, dtype=torch.float64, device=self.dev)
         _lib.call("omb_gram_combine", _p(Gf), F, m, _p(self.scl if scaled else None), _p(G), st)
         if self.world > 1:                          # fixed order: identical bits on every rank
-            G = _comm.ordered_sum(self.comm.allgather(G)).view(m, m)
+            G = self.comm.sum_ordered(G)
         return G
 
     def eig_pod(self, G):
@@ -293,7 +301,7 @@ class Engine:
         _lib.call("omb_gram", _p(U1), 1, self.n_loc, r, None, _p(Gf), _p(ws), _stream())
         H = Gf.view(r, r)
         if self.world > 1:
-            H = _comm.ordered_sum(self.comm.allgather(H.contiguous())).view(r, r)
+            H = self.comm.sum_ordered(H.contiguous())
         return H, U1
 
     def basis_rotate(self, U1, M):
@@ -426,7 +434,7 @@ class Engine:
         _lib.call("omb_gather_rows", _p(self.Ut), self.r, _p(loc), s, _p(Theta), _p(self.cnt), _p(cnt_s),
                   _stream())
         both = torch.cat([Theta * mine.unsqueeze(1), (cnt_s * mine).unsqueeze(1)], dim=1)
-        both = _comm.ordered_sum(self.comm.allgather(both)).view(s, self.r + 1)   # one non-zero term per row
+        both = self.comm.sum_ordered(both.contiguous())                  # one non-zero term per row
         return both[:, : self.r].contiguous(), both[:, self.r].contiguous()
 
     def ols_predict(self, Y_dev, cnt_s, scl_s, PinvT):

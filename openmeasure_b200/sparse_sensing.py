@@ -16,8 +16,8 @@ Deliberate differences (DESIGN.md "Reference quirks"):
   * X0 and Ur are materialised on the host only when read;
   * POD modes are defined up to sign (as in any SVD); singular values/reconstructions agree with
     the reference to 1e-10, pivots are identical on non-degenerate inputs.
-Out of scope (raise NotImplementedError): GEM placement, constrained OLS ('COLS'), CPOD,
-adaptive_sampling, scale_limits -- see SURVEY.md section 8.
+Out of scope (raise NotImplementedError): constrained OLS ('COLS'), CPOD, adaptive_sampling,
+scale_limits -- see SURVEY.md section 8.
 """
 import numpy as np
 import torch
@@ -86,6 +86,33 @@ def _as_pivots(C):
     return None
 
 
+def _upload_blocks(X, n_features):
+    """Host snapshot matrix -> HBM.  A pinned matrix is uploaded one feature block at a time on a copy
+    stream and the per-block arrival events are returned: the engine's first stage consumes the blocks
+    as they land (Engine.stats), so the statistics / Gram passes overlap the PCIe transfer instead of
+    following it.  Pageable memory: one synchronous copy, arrival = None."""
+    if X.dtype != np.float64 or not X.flags.c_contiguous:
+        X = np.ascontiguousarray(X, dtype=np.float64)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Xd = torch.empty(X.shape, dtype=torch.float64, device=dev)
+    Xh = torch.from_numpy(X)
+    F, n_c = n_features, X.shape[0] // n_features
+    if not (Xh.is_pinned() and F > 1):
+        Xd.copy_(Xh, non_blocking=True)
+        return Xd, None
+    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream.wait_stream(torch.cuda.current_stream(dev))
+    arrival = []
+    with torch.cuda.stream(copy_stream):
+        for f in range(F):
+            Xd[f * n_c:(f + 1) * n_c].copy_(Xh[f * n_c:(f + 1) * n_c], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            arrival.append(ev)
+    Xd.record_stream(copy_stream)
+    return Xd, arrival
+
+
 class ROM:
     """Reduced-order-model utilities: centring/scaling, POD, truncation, reconstruction
     (reference ROM, sparse_sensing.py:18-511)."""
@@ -145,35 +172,30 @@ class ROM:
         Xd = ingest.load_npy_shard(path, n_features, rank, world)
         return cls.from_device(Xd, n_features, xyz, group=group)
 
+    @classmethod
+    def from_host(cls, X_host, n_features, xyz=None, group=None):
+        """Extension: one rank's HOST shard of a row-sharded problem (numpy float64 (F*n_c_loc, m): this
+        rank's cells [c0, c0 + n_c_loc) of every feature; pinned memory makes the upload asynchronous).
+        The same upload path as the plain constructor -- feature blocks cross PCIe on a copy stream while
+        the statistics / Gram passes consume the blocks that have landed -- followed by from_device()."""
+        if type(X_host) is not np.ndarray:
+            raise TypeError('The matrix X is not a numpy array.')
+        if type(n_features) is not int:
+            raise TypeError('The parameter n_features is not an integer.')
+        if X_host.shape[0] % n_features != 0:
+            raise Exception('The number of rows of X is not a multiple of n_features')
+        _eng.require_cuda()
+        Xd, arrival = _upload_blocks(X_host, n_features)
+        self = cls.from_device(Xd, n_features, xyz, group=group)
+        self._eng._arrival = arrival
+        return self
+
     def _engine(self):
         if self._eng is None:
             _eng.require_cuda()
-            X = self.X
-            if X.dtype != np.float64 or not X.flags.c_contiguous:
-                X = np.ascontiguousarray(X, dtype=np.float64)
-            dev = torch.device("cuda", torch.cuda.current_device())
-            Xd = torch.empty(X.shape, dtype=torch.float64, device=dev)
-            Xh = torch.from_numpy(X)
-            F, n_c = self.n_features, X.shape[0] // self.n_features
-            if Xh.is_pinned() and F > 1:
-                # pinned host matrix: upload one feature block at a time on a copy stream; the engine's
-                # first stage consumes the blocks as they land (Engine.stats), so the statistics / Gram
-                # passes overlap the PCIe transfer instead of following it
-                copy_stream = torch.cuda.Stream(device=dev)
-                copy_stream.wait_stream(torch.cuda.current_stream(dev))
-                arrival = []
-                with torch.cuda.stream(copy_stream):
-                    for f in range(F):
-                        Xd[f * n_c:(f + 1) * n_c].copy_(Xh[f * n_c:(f + 1) * n_c], non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(copy_stream)
-                        arrival.append(ev)
-                Xd.record_stream(copy_stream)
-                self._eng = _eng.Engine(Xd, self.n_features, group=False)
-                self._eng._arrival = arrival
-            else:
-                Xd.copy_(Xh, non_blocking=True)
-                self._eng = _eng.Engine(Xd, self.n_features, group=False)
+            Xd, arrival = _upload_blocks(self.X, self.n_features)
+            self._eng = _eng.Engine(Xd, self.n_features, group=False)
+            self._eng._arrival = arrival
         return self._eng
 
     def _n_rows(self):
@@ -238,6 +260,8 @@ class ROM:
                              '(same failure as the reference for this option)')
         eng = self._engine()
         if scale_type == 'median':
+            if eng.world > 1:        # np.median over the WHOLE feature block (:140): a local median per rank is wrong
+                raise NotImplementedError("scale_type='median' needs the whole feature block on one rank")
             eng.stats('none', axis_cnt, defer_row_means)
             blocks = eng.X.view(eng.F, -1)
             k = blocks.shape[1]
@@ -415,8 +439,17 @@ class ROM:
         self.Vr = Ar / sig
 
     # ------------------------------------------------------------------ reconstruct (a11)
-    def reconstruct(self, Ar, sampling=None):
-        """X_rec (n, N) = unscale(Ur @ Ar.T) (sparse_sensing.py:342-375)."""
+    def reconstruct(self, Ar, sampling=None, *, out=None, chunk_rows=None):
+        """X_rec (n, N) = unscale(Ur @ Ar.T) (sparse_sensing.py:342-375).
+
+        The n x N result never exists on the device: row chunks of it are produced by the GEMM kernel
+        into two device buffers and leave through two pinned host buffers while the next chunk is
+        computed (config 4: 16.2M rows x 65 536 vectors = 8.5 TB).  Extensions (keyword-only):
+          out         None: a new (n, N) numpy array is returned, like the reference;
+                      an ndarray / np.memmap of shape (n, N): filled in place and returned;
+                      a callable out(row0, block): called once per chunk with a (rows, N) view that is
+                      only valid during the call (streams to disk, a socket, a reduction ...); returns None
+          chunk_rows  rows per chunk (multiple of 128; default: ~256 MB of output per chunk)"""
         Ar = np.asarray(Ar, dtype=np.float64)
         if Ar.ndim < 2:
             Ar = Ar[np.newaxis, :]
@@ -425,7 +458,72 @@ class ROM:
         if sampling is not None:                          # :365-368: (S Ur) Ar^T, sampled unscaling
             SU, scl_s, cnt_s = self._sampled(sampling)
             return (scl_s[:, None] * (SU @ Ad.T) + cnt_s[:, None]).cpu().numpy()
-        return eng.reconstruct(Ad).cpu().numpy()
+        n, N = eng.n_loc, int(Ad.shape[0])
+        sink = out if callable(out) else None
+        if sink is None:
+            if out is None:
+                out = np.empty((n, N))
+            elif out.shape != (n, N) or out.dtype != np.float64:
+                raise ValueError('out must be a float64 array of shape (n, N)')
+        for row0, block in self.reconstruct_chunks(Ad, chunk_rows=chunk_rows):
+            if sink is not None:
+                sink(row0, block)
+            else:
+                out[row0:row0 + block.shape[0]] = block
+        return None if sink is not None else out
+
+    def reconstruct_chunks(self, Ar, chunk_rows=None):
+        """Generator over (row0, block): block = rows [row0, row0 + rows) of the reconstruction as a
+        (rows, N) numpy view of a pinned host buffer, valid until the next iteration.  Two device
+        buffers and two pinned buffers: chunk k+1 is computed while chunk k crosses PCIe."""
+        eng = self._engine()
+        if torch.is_tensor(Ar):
+            Ad = Ar.to(eng.dev, torch.float64)
+        else:
+            Ar = np.asarray(Ar, dtype=np.float64)
+            Ad = torch.from_numpy(np.ascontiguousarray(Ar[np.newaxis, :] if Ar.ndim < 2 else Ar)).to(eng.dev)
+        if Ad.shape[1] != eng.r:
+            raise ValueError('The number of columns of Ar does not match the number of modes.')
+        n, N = eng.n_loc, int(Ad.shape[0])
+        if chunk_rows is None:
+            chunk_rows = max(128, ((256 << 20) // (8 * N)) // 128 * 128)
+        chunk_rows = int(min(max(128, (int(chunk_rows) + 127) // 128 * 128), (n + 127) // 128 * 128))
+        nbuf = 1 if chunk_rows >= n else 2
+        key = (chunk_rows, N, nbuf)
+        st = getattr(self, "_recon_ring", None)
+        if st is None or st["key"] != key:
+            st = {"key": key,
+                  "dev": [torch.empty(chunk_rows, N, dtype=torch.float64, device=eng.dev) for _ in range(nbuf)],
+                  "host": [torch.empty(chunk_rows, N, dtype=torch.float64, pin_memory=chunk_rows * N >= (1 << 17))
+                           for _ in range(nbuf)],
+                  "copy": torch.cuda.Stream(device=eng.dev)}
+            self._recon_ring = st
+        cur = torch.cuda.current_stream(eng.dev)
+        copy = st["copy"]
+        done = [None] * nbuf          # D2H of the buffer's previous chunk finished
+        pending = None                # (row0, rows, buffer) of the chunk in flight to the host
+        for k, row0 in enumerate(range(0, n, chunk_rows)):
+            b = k % nbuf
+            rows = min(chunk_rows, n - row0)
+            if done[b] is not None:
+                cur.wait_event(done[b])                   # the device buffer is free again
+            eng.reconstruct(Ad, row0=row0, nrows=rows, out=st["dev"][b])
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            if pending is not None:                       # hand the previous chunk to the caller while
+                p0, prow, pb = pending                    # this one is being computed
+                done[pb].synchronize()
+                yield p0, st["host"][pb][:prow].numpy()
+            copy.wait_event(ready)
+            with torch.cuda.stream(copy):
+                st["host"][b][:rows].copy_(st["dev"][b][:rows], non_blocking=True)
+                done[b] = torch.cuda.Event()
+                done[b].record(copy)
+            pending = (row0, rows, b)
+        if pending is not None:
+            p0, prow, pb = pending
+            done[pb].synchronize()
+            yield p0, st["host"][pb][:prow].numpy()
 
     # ------------------------------------------------------------------ out of scope
     def scale_limits(self, limits):
