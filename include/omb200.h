@@ -61,6 +61,14 @@ int omb_synth_fill(double* d_X, int64_t F, int64_t n_cells, int64_t cell0, int64
  *      n_cells-row feature blocks, sparse_sensing.py:112-161) -------------------------------- */
 /* Row means with numpy's pairwise tree (bit-exact): d_cnt[i] = mean(X[i, :]).  rows = F*n_c. */
 int omb_row_means(const double* d_X, int64_t rows, int64_t m, double* d_cnt, void* stream);
+/* Centred copy for the many-snapshot (m > 64) contraction kernels: d_X0c[i][j] = X[i][j] - cnt[i].
+ * compute_means != 0: cnt[i] = np.average(X[i, :]) (bit-exact, written to d_cnt) from the same pass -- HBM sees
+ * one read of X and one write of X0c; compute_means == 0: d_cnt is given (axis_cnt=None: block means).
+ * Replaces the (X - X_cnt) temporary of sparse_sensing.py:169 for the tensor-core passes, which then run
+ * without a single FP64 add in their inner loops (DADD shares the FP64 pipe with DMMA).  m even; X, X0c
+ * 16-byte aligned. */
+int omb_center_rows(const double* d_X, int64_t rows, int64_t m, int compute_means, double* d_cnt,
+                    double* d_X0c, void* stream);
 /* Per-feature block reductions with numpy's pairwise tree over the n_c*m contiguous elements:
  *   mode 0: d_out[f*4 + {0,1,2}] = {sum, min, max}
  *   mode 1: d_out[f*4 + 3]       = sum((x - d_out[f*4+0]/mean_count)^2)   (np.std's second pass;

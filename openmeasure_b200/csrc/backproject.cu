@@ -276,195 +276,239 @@ static int launch_bp_small(const double* X, int64_t n, int64_t n_c, int m, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Many-snapshot / many-mode variant (m or r > 64; m, r even): persistent, TMA-pipelined.
-// One CTA per SM walks the 128-row basis tiles.  32-snapshot K-chunks of the tile's rows of X (one
-// 256-byte bulk copy per row, padded pitch 36 doubles -> conflict-free fragment loads) and of W
-// flow through a 3-stage ring; every warp issues its own share of a chunk's copies two chunks
-// ahead (also across tile boundaries, so the epilogue of a tile overlaps the loads of the next).
-// 8 warps = 4 row groups x 2 column halves, 32 x 8*QH outputs each (up to 128 accumulator
-// registers per lane -- hence 256 threads, not a ninth producer warp: 288 threads cap ptxas at
-// 168 registers).  The epilogue needs no staging: a DMMA accumulator fragment is eight
-// consecutive candidates of one mode, i.e. one 64-byte run of the tiled mode-major layout.
+// Many-snapshot / many-mode variant (m or r > 64; m, r even): persistent, warp-specialised, TMA-fed.
+// One CTA per SM walks the 128-row basis tiles.  A producer warp streams 32-snapshot K-chunks of the
+// tile's rows of X (one 256-byte bulk copy per row, padded pitch 36 doubles -> conflict-free fragment
+// loads) and of W through a 3-stage ring; it belongs to a third warpgroup that hands its registers
+// to the MMA warps (setmaxnreg), so those hold their accumulators AND double-buffered fragments
+// without a producer's issue code on their critical path.
+// 8 MMA warps x (16 rows x all 8*QB modes of the launch): every A fragment is loaded by exactly one
+// warp (2 + QB fragment loads for 2*QB DMMAs per k-step), a row's modes all live in one warp -- the
+// placement norms need no cross-warp step -- and 8*QB >= r is padded to the next multiple of 8, not
+// 16 (r = 100: 104 columns computed instead of 112).
+// CENTRE = false: X is the centred copy the Gram pass left behind (Engine._X0c), the k-step is
+// LDS + DMMA only.  CENTRE = true (no room for the copy): x - cnt on the two A fragments per k-step.
+// The epilogue needs no staging: a DMMA accumulator fragment is eight consecutive candidates of one
+// mode, i.e. one 64-byte run of the tiled mode-major layout.
 // ---------------------------------------------------------------------------------------------
 constexpr int BB_K = 32;                    // snapshots per stage
 constexpr int BB_LDA = BB_K + 4;            // == 4 (mod 16)
 constexpr int BB_STAGES = 3;
-constexpr int BB_WARPS = 8;
-constexpr int BB_THREADS = BB_WARPS * 32;
+constexpr int BB_MMA_WARPS = 8;
+constexpr int BB_THREADS = (BB_MMA_WARPS + 4) * 32;
 
-template <int QH>
+template <int QB>
 struct BbCfg {
-    static constexpr int QC = 16 * QH;                   // modes per launch
-    static constexpr int LDW = QC + 4;                   // == 4 (mod 16)
+    static constexpr int QC = 8 * QB;                    // modes per launch
+    static constexpr int LDW = QC + 4;                   // == 4 (mod 8): k rows 4 apart never share a bank pair
     static constexpr int STAGE = OMB_TB * BB_LDA + BB_K * LDW;
-    static constexpr size_t BYTES = sizeof(double) * ((size_t)BB_STAGES * STAGE + 2 * OMB_TB);
+    static constexpr size_t BYTES = sizeof(double) * (size_t)BB_STAGES * STAGE;
 };
 
-template <int QH>
-__global__ void __launch_bounds__(BB_THREADS)
+template <int QB>
+struct BbFrag { double a0, a1, b[QB]; };
+
+template <int QB>
+__device__ __forceinline__ void bb_load(BbFrag<QB>& f, const double* sA, const double* sW, int k4, int fr, int fc, int ib)
+{
+    const int kk = k4 * 4 + fr;
+    f.a0 = sA[(ib + fc) * BB_LDA + kk];
+    f.a1 = sA[(ib + 8 + fc) * BB_LDA + kk];
+    const double* wr = sW + kk * BbCfg<QB>::LDW + fc;
+#pragma unroll
+    for (int q = 0; q < QB; ++q) f.b[q] = wr[8 * q];
+}
+
+template <int QB, bool CENTRE>
+__global__ void __launch_bounds__(BB_THREADS, 1)
 backproject_big_kernel(const double* __restrict__ X, int64_t n, int64_t n_c, int m, const double* __restrict__ cnt,
                        const double* __restrict__ scl, const double* __restrict__ W, int r, int q0, int first, int last,
                        double* __restrict__ Ut, double* __restrict__ vn)
 {
-    using Cfg = BbCfg<QH>;
+    using Cfg = BbCfg<QB>;
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t full_bar[BB_STAGES], empty_bar[BB_STAGES];
-    double* s_n = smem + (size_t)BB_STAGES * Cfg::STAGE;         // [2][128] row sums of squares per column half
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t ntiles = basis_tiles(n);
     const int nch = (m + BB_K - 1) / BB_K;
     const int qv = (r - q0) < Cfg::QC ? (r - q0) : Cfg::QC;      // valid modes of this launch (even)
 
+    // rows / snapshots / modes beyond the matrix are never written by the copies: zero the ring once
     for (int e = threadIdx.x; e < BB_STAGES * Cfg::STAGE; e += BB_THREADS) smem[e] = 0.0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BB_STAGES; ++s) { mbar_init(&full_bar[s], BB_WARPS); mbar_init(&empty_bar[s], BB_WARPS); }
+        for (int s = 0; s < BB_STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], BB_MMA_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
     __syncthreads();
 
-    // ---- issue side: this warp's share (16 rows of X, 4 rows of W) of chunk `gi`
-    int64_t it_tile = blockIdx.x, gi = 0;
-    int it_c = 0;
-    auto issue = [&]() {
-        if (it_tile >= ntiles) return;
-        const int s = (int)(gi % BB_STAGES);
-        if (gi >= BB_STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((gi / BB_STAGES) - 1) & 1));
-        const int64_t row0 = it_tile * OMB_TB;
-        const int rows = (int)((n - row0) < OMB_TB ? (n - row0) : OMB_TB);
-        const int k0 = it_c * BB_K;
-        const int kv = (m - k0) < BB_K ? (m - k0) : BB_K;
-        int nx = rows - 16 * warp; nx = nx < 0 ? 0 : (nx > 16 ? 16 : nx);
-        int nw = kv - 4 * warp; nw = nw < 0 ? 0 : (nw > 4 ? 4 : nw);
-        double* sA = smem + (size_t)s * Cfg::STAGE;
-        double* sW = sA + OMB_TB * BB_LDA;
-        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(((int64_t)nx * kv + (int64_t)nw * qv) * sizeof(double)));
-        __syncwarp();
-        if (lane < nx) {
-            const int rr = 16 * warp + lane;
-            tma_load_bulk(sA + rr * BB_LDA, X + (row0 + rr) * m + k0, (uint32_t)(kv * sizeof(double)), &full_bar[s]);
-        } else if (lane >= 16 && lane - 16 < nw) {
-            const int kk = 4 * warp + lane - 16;
-            tma_load_bulk(sW + kk * Cfg::LDW, W + (int64_t)(k0 + kk) * r + q0, (uint32_t)(qv * sizeof(double)), &full_bar[s]);
+    if (warp >= BB_MMA_WARPS) {
+        // =========================== producer warpgroup ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        // every bulk copy is its own (warp-serialised) instruction, ~60 cycles each: one warp cannot issue the 160
+        // copies of a chunk in the time the MMA warps need for it, four can.  Producer warp p: rows [32p, 32p + 32)
+        // of the tile (one per lane) and rows [8p, 8p + 8) of the W chunk.
+        const int pw = warp - BB_MMA_WARPS;
+        int s = 0;
+        uint32_t ph = 0;
+        bool wrapped = false;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t row0 = tile * OMB_TB;
+            const int rows = (int)((n - row0) < OMB_TB ? (n - row0) : OMB_TB);
+            int nx = rows - 32 * pw; nx = nx < 0 ? 0 : (nx > 32 ? 32 : nx);
+            for (int c = 0; c < nch; ++c) {
+                if (wrapped) mbar_wait(&empty_bar[s], ph ^ 1);
+                const int k0 = c * BB_K;
+                const int kv = (m - k0) < BB_K ? (m - k0) : BB_K;
+                int nw = kv - 8 * pw; nw = nw < 0 ? 0 : (nw > 8 ? 8 : nw);
+                double* sA = smem + (size_t)s * Cfg::STAGE;
+                double* sW = sA + OMB_TB * BB_LDA;
+                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(((int64_t)nx * kv + (int64_t)nw * qv) * sizeof(double)));
+                __syncwarp();
+                if (lane < nx) {
+                    const int rr = 32 * pw + lane;
+                    tma_load_bulk(sA + rr * BB_LDA, X + (row0 + rr) * m + k0, (uint32_t)(kv * sizeof(double)), &full_bar[s]);
+                }
+                if (lane < nw) {
+                    const int kk = 8 * pw + lane;
+                    tma_load_bulk(sW + kk * Cfg::LDW, W + (int64_t)(k0 + kk) * r + q0, (uint32_t)(qv * sizeof(double)), &full_bar[s]);
+                }
+                if (++s == BB_STAGES) { s = 0; ph ^= 1; wrapped = true; }
+            }
         }
-        ++gi;
-        if (++it_c == nch) { it_c = 0; it_tile += gridDim.x; }
-    };
-#pragma unroll 1
-    for (int u = 0; u < BB_STAGES - 1; ++u) issue();
+        return;
+    }
 
-    // ---- compute side: warp (wr, wc) owns rows [32 wr, +32) x modes [8 QH wc, +8 QH)
+    // =============================== MMA warps ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int fr = lane & 3, fc = lane >> 2;
-    const int wr = warp >> 1, wc = warp & 1;
-    const int ib = wr * 32, jb = wc * 8 * QH;
-    int64_t g = 0;
+    const int ib = warp * 16;
+    int s = 0;
+    uint32_t ph = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * OMB_TB;
-        double cv[4], sv[4];
-        bool rok[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int64_t row = row0 + ib + 8 * p + fc;
-            rok[p] = row < n;
-            cv[p] = (rok[p] && cnt) ? cnt[row] : 0.0;
-            sv[p] = (rok[p] && scl) ? scl[row / n_c] : 1.0;
+        const int64_t ra = row0 + ib + fc, rb = ra + 8;
+        const bool oka = ra < n, okb = rb < n;
+        double ca = 0.0, cb = 0.0;
+        if (CENTRE) {
+            ca = (oka && cnt) ? cnt[ra] : 0.0;
+            cb = (okb && cnt) ? cnt[rb] : 0.0;
         }
-        double acc[4][QH][2];
+        const double sa = (oka && scl) ? scl[ra / n_c] : 1.0, sb = (okb && scl) ? scl[rb / n_c] : 1.0;
+        double acc[2][QB][2];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int p = 0; p < 2; ++p)
 #pragma unroll
-            for (int q = 0; q < QH; ++q) acc[p][q][0] = acc[p][q][1] = 0.0;
+            for (int q = 0; q < QB; ++q) acc[p][q][0] = acc[p][q][1] = 0.0;
 
+        BbFrag<QB> f[2];
+        mbar_wait(&full_bar[s], ph);
+        bb_load<QB>(f[0], smem + (size_t)s * Cfg::STAGE, smem + (size_t)s * Cfg::STAGE + OMB_TB * BB_LDA, 0, fr, fc, ib);
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c, ++g) {
-            issue();                                           // chunk g + 2 into the stage chunk g - 1 used
-            const int s = (int)(g % BB_STAGES);
-            mbar_wait(&full_bar[s], (uint32_t)((g / BB_STAGES) & 1));
+        for (int c = 0; c < nch; ++c) {
             const double* sA = smem + (size_t)s * Cfg::STAGE;
             const double* sW = sA + OMB_TB * BB_LDA;
+            const int s0 = s;
+            const bool more = c + 1 < nch;
             const int kv = (m - c * BB_K) < BB_K ? (m - c * BB_K) : BB_K;
+            if (++s == BB_STAGES) { s = 0; ph ^= 1; }
 #pragma unroll
             for (int k4 = 0; k4 < BB_K / 4; ++k4) {
-                const int kk = k4 * 4 + fr;
-                const bool kok = kk < kv;                      // stale snapshots of a ragged last chunk
-                double a[4], b[QH];
+                if (k4 + 1 < BB_K / 4) bb_load<QB>(f[(k4 + 1) & 1], sA, sW, k4 + 1, fr, fc, ib);
+                else if (more) {                              // first fragments of the next chunk
+                    mbar_wait(&full_bar[s], ph);
+                    bb_load<QB>(f[0], smem + (size_t)s * Cfg::STAGE, smem + (size_t)s * Cfg::STAGE + OMB_TB * BB_LDA, 0, fr, fc, ib);
+                }
+                BbFrag<QB>& g = f[k4 & 1];
+                if (CENTRE) {
+                    const bool kok = (k4 * 4 + fr) < kv;       // stale snapshots of a ragged last chunk (W rows are zero too)
+                    g.a0 = kok ? g.a0 - ca : 0.0;
+                    g.a1 = kok ? g.a1 - cb : 0.0;
+                } else if (k4 * 4 + 3 >= kv) {                 // ragged last chunk: columns kv.. hold stale data
+                    const bool kok = (k4 * 4 + fr) < kv;
+                    g.a0 = kok ? g.a0 : 0.0;
+                    g.a1 = kok ? g.a1 : 0.0;
+                }
 #pragma unroll
-                for (int p = 0; p < 4; ++p) a[p] = sA[(ib + 8 * p + fc) * BB_LDA + kk];
-#pragma unroll
-                for (int q = 0; q < QH; ++q) b[q] = sW[kk * Cfg::LDW + jb + 8 * q + fc];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) a[p] = kok ? a[p] - cv[p] : 0.0;
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-#pragma unroll
-                    for (int q = 0; q < QH; ++q) dmma884(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+                for (int q = 0; q < QB; ++q) {
+                    dmma884(acc[0][q][0], acc[0][q][1], g.a0, g.b[q]);
+                    dmma884(acc[1][q][0], acc[1][q][1], g.a1, g.b[q]);
+                }
             }
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s0])) : "memory");
         }
 
-        // epilogue: U = acc / scl straight to the tile (64-byte runs), row sums of squares for the norms
-        double* tbase = Ut + tile * ((int64_t)r * OMB_TB);
+        // epilogue: U = acc / scl straight to the tile (64-byte runs); the row's sum of squares for the norms
+        double* tbase = Ut + tile * ((int64_t)r * OMB_TB) + ib + fc;
+        const double isa = 1.0 / sa, isb = 1.0 / sb;             // one division per row, not per element
+        double ssa = 0.0, ssb = 0.0;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int i = ib + 8 * p + fc;
-            const double isv = 1.0 / sv[p];                    // one division per row, not per element
-            double ss = 0.0;
+        for (int q = 0; q < QB; ++q) {
 #pragma unroll
-            for (int q = 0; q < QH; ++q) {
-                const int col = jb + 8 * q + 2 * fr;           // mode index inside this launch
-                const double u0 = acc[p][q][0] * isv, u1 = acc[p][q][1] * isv;
-                if (col < qv) { if (rok[p]) stg_stream(tbase + (int64_t)(q0 + col) * OMB_TB + i, u0); ss = fma(u0, u0, ss); }
-                if (col + 1 < qv) { if (rok[p]) stg_stream(tbase + (int64_t)(q0 + col + 1) * OMB_TB + i, u1); ss = fma(u1, u1, ss); }
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * q + 2 * fr + e;               // mode index inside this launch
+                if (col < qv) {
+                    const double ua = acc[0][q][e] * isa, ub = acc[1][q][e] * isb;
+                    double* dst = tbase + (int64_t)(q0 + col) * OMB_TB;
+                    if (oka) stg_stream(dst, ua);
+                    if (okb) stg_stream(dst + 8, ub);
+                    ssa = fma(ua, ua, ssa);
+                    ssb = fma(ub, ub, ssb);
+                }
             }
-            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 1);
-            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 2);
-            if (vn && fr == 0) s_n[wc * OMB_TB + i] = ss;
         }
         if (vn) {
-            __syncthreads();
-            if (threadIdx.x < OMB_TB && row0 + threadIdx.x < n) {
-                double t = s_n[threadIdx.x] + s_n[OMB_TB + threadIdx.x];
-                double* dst = vn + row0 + threadIdx.x;
-                if (!first) t += *dst;
-                *dst = last ? sqrt(t) : t;
+            ssa += __shfl_xor_sync(0xFFFFFFFFu, ssa, 1); ssa += __shfl_xor_sync(0xFFFFFFFFu, ssa, 2);
+            ssb += __shfl_xor_sync(0xFFFFFFFFu, ssb, 1); ssb += __shfl_xor_sync(0xFFFFFFFFu, ssb, 2);
+            if (fr == 0) {
+                if (oka) { double t = ssa; if (!first) t += vn[ra]; vn[ra] = last ? sqrt(t) : t; }
+                if (okb) { double t = ssb; if (!first) t += vn[rb]; vn[rb] = last ? sqrt(t) : t; }
             }
-            __syncthreads();
         }
     }
 }
 
-template <int QH>
+template <int QB, bool CENTRE>
 static int launch_bp_big(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl,
                          const double* W, int r, int q0, double* Ut, double* vn, cudaStream_t st)
 {
-    using Cfg = BbCfg<QH>;
-    OMB_CUDA(cudaFuncSetAttribute(backproject_big_kernel<QH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::BYTES));
+    using Cfg = BbCfg<QB>;
+    OMB_CUDA(cudaFuncSetAttribute(backproject_big_kernel<QB, CENTRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::BYTES));
     int64_t grid = basis_tiles(n);
     if (grid > sm_count()) grid = sm_count();
     const int first = q0 == 0, last = q0 + Cfg::QC >= r;
-    backproject_big_kernel<QH><<<(unsigned)grid, BB_THREADS, Cfg::BYTES, st>>>(X, n, n_c, m, cnt, scl, W, r, q0, first, last, Ut, vn);
+    backproject_big_kernel<QB, CENTRE><<<(unsigned)grid, BB_THREADS, Cfg::BYTES, st>>>(X, n, n_c, m, cnt, scl, W, r, q0, first, last, Ut, vn);
     return check_launch("backproject_big_kernel");
 }
 
-static int bp_big(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl, const double* W,
-                  int r, double* Ut, double* vn, cudaStream_t st)
+template <bool CENTRE>
+static int bp_big_t(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl, const double* W,
+                    int r, double* Ut, double* vn, cudaStream_t st)
 {
     // launches of up to 128 modes; the last one takes the narrowest instantiation that fits
     for (int q0 = 0; q0 < r; q0 += 128) {
         const int rem = r - q0;
-        const int qh = rem >= 128 ? 8 : (rem + 15) / 16;
+        const int qb = rem >= 128 ? 16 : (rem + 7) / 8;
         int rc;
-        switch (qh) {
-#define OMB_BB(QHV) case QHV: rc = launch_bp_big<QHV>(X, n, n_c, m, cnt, scl, W, r, q0, Ut, vn, st); break;
+        switch (qb) {
+#define OMB_BB(QBV) case QBV: rc = launch_bp_big<QBV, CENTRE>(X, n, n_c, m, cnt, scl, W, r, q0, Ut, vn, st); break;
             OMB_BB(1) OMB_BB(2) OMB_BB(3) OMB_BB(4) OMB_BB(5) OMB_BB(6) OMB_BB(7) OMB_BB(8)
+            OMB_BB(9) OMB_BB(10) OMB_BB(11) OMB_BB(12) OMB_BB(13) OMB_BB(14) OMB_BB(15) OMB_BB(16)
 #undef OMB_BB
             default: rc = -1; break;
         }
         if (rc) return rc;
     }
     return 0;
+}
+
+static int bp_big(const double* X, int64_t n, int64_t n_c, int m, const double* cnt, const double* scl, const double* W,
+                  int r, double* Ut, double* vn, cudaStream_t st)
+{
+    return cnt ? bp_big_t<true>(X, n, n_c, m, cnt, scl, W, r, Ut, vn, st)
+               : bp_big_t<false>(X, n, n_c, m, cnt, scl, W, r, Ut, vn, st);
 }
 
 }  // namespace omb

@@ -174,7 +174,7 @@ __device__ __forceinline__ void track_minmax(double x, double& lo, double& hi)
 // Every lane of the quad returns the result.  `vec`: the leaf is 16-byte aligned.
 template <class Map, bool MINMAX>
 __device__ __forceinline__ double leaf_sum_quad(const double* __restrict__ a, int n, int q, unsigned qmask, bool vec,
-                                                Map f, double& lo, double& hi)
+                                                Map f, double& lo, double& hi, double2* keep = nullptr)
 {
     if (n < 8) {
         double res = -0.0;
@@ -196,6 +196,10 @@ __device__ __forceinline__ double leaf_sum_quad(const double* __restrict__ a, in
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if (i < noct) { x[i].x = ldg_stream(p + 8 * i); x[i].y = ldg_stream(p + 8 * i + 1); }
+    }
+    if (keep) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) keep[i] = x[i];
     }
     double r0 = 0.0, r1 = 0.0;
 #pragma unroll
@@ -289,8 +293,10 @@ block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LW, int
 // Row means for rows of up to 1024 snapshots: the block-tree machinery applied per row.  A row's
 // numpy tree has S = 2^D <= 8 leaf slots; a warp evaluates 8 / S rows at once, one quad per slot
 // (128-bit loads, up to 256 bytes in flight per lane), and combines a row's slots by shuffles.
-__global__ void __launch_bounds__(BS_THREADS, BS_CTAS_PER_SM)
-row_means_quad_kernel(const double* __restrict__ X, int64_t rows, int m, int D, double* __restrict__ cnt)
+template <bool COPY>
+__global__ void __launch_bounds__(BS_THREADS, COPY ? 4 : BS_CTAS_PER_SM)
+row_means_quad_kernel(const double* __restrict__ X, int64_t rows, int m, int D, double* __restrict__ cnt,
+                      double* __restrict__ X0c)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane & 3, sl = lane >> 2;
@@ -306,10 +312,11 @@ row_means_quad_kernel(const double* __restrict__ X, int64_t rows, int m, int D, 
         bool here = row < rows;
         if (here) here = descend(off, n, (uint32_t)(sl & (S - 1)), D);
         double v = 0.0, lo = 0.0, hi = 0.0;
+        double2 keep[16];
         if (here) {
             const double* a = X + row * m + off;
             const bool vec = xal && (((row * m) & 1) == 0);
-            v = leaf_sum_quad<MapId, false>(a, (int)n, q, qmask, vec, MapId(), lo, hi);
+            v = leaf_sum_quad<MapId, false>(a, (int)n, q, qmask, vec, MapId(), lo, hi, COPY ? keep : nullptr);
         }
         const unsigned hb = __ballot_sync(0xFFFFFFFFu, here);
         unsigned pres = 0;
@@ -318,7 +325,46 @@ row_means_quad_kernel(const double* __restrict__ X, int64_t rows, int m, int D, 
         if (S > 1) v = upsweep_level(v, sl, 1, 4, pres);
         if (S > 2) v = upsweep_level(v, sl, 2, 4, pres);
         if (S > 4) v = upsweep_level(v, sl, 4, 4, pres);
-        if (q == 0 && (sl & (S - 1)) == 0 && row < rows) cnt[row] = v / dm;
+        const double mean = v / dm;
+        if (q == 0 && (sl & (S - 1)) == 0 && row < rows) cnt[row] = mean;
+        if (COPY) {
+            // centred copy X0c = X - mean for the many-snapshot contraction kernels (m even, X 16-byte aligned),
+            // straight from the registers the leaf sums were formed from: HBM sees one read of X and one write of
+            // X0c.  DADD shares the FP64 pipe with DMMA -- centring inside the tensor-core kernels, once per tile an
+            // element takes part in, cost them a quarter of the pipe.
+            const double mr = __shfl_sync(0xFFFFFFFFu, mean, 4 * ((sl >> D) << D));     // the mean of this lane's row
+            if (here) {
+                double* dst = X0c + row * m + off;
+                const int noct = (n >= 8) ? (int)(n >> 3) : 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (i < noct) {
+                        double2 x = keep[i];
+                        x.x -= mr; x.y -= mr;
+                        stg_stream2(dst + 8 * i + 2 * q, x);
+                    }
+                }
+                if (q == 0) {
+                    const double* a = X + row * m + off;
+                    for (int i = noct * 8; i < (int)n; ++i) dst[i] = a[i] - mr;       // ragged tail of the leaf
+                }
+            }
+        }
+    }
+}
+
+// X0c[i][j] = X[i][j] - cnt[i]  (centring values given: block means, or row means of wide rows)
+__global__ void __launch_bounds__(256)
+center_given_kernel(const double* __restrict__ X, int64_t rows, int64_t m, const double* __restrict__ cnt,
+                    double* __restrict__ X0c)
+{
+    const int64_t half = m >> 1, total = rows * half;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / half;
+        const double c = cnt[row];
+        double2 x = ldg_stream2(X + 2 * e);
+        x.x -= c; x.y -= c;
+        stg_stream2(X0c + 2 * e, x);
     }
 }
 
@@ -461,7 +507,7 @@ extern "C" int omb_row_means(const double* d_X, int64_t rows, int64_t m, double*
         int64_t g = ceil_div(ceil_div(rows, (int64_t)(8 >> rp.D)), BS_THREADS / 32);
         const int64_t cap2 = (int64_t)sm_count() * BS_CTAS_PER_SM;
         if (g > cap2) g = cap2;
-        row_means_quad_kernel<<<(unsigned)g, BS_THREADS, 0, (cudaStream_t)stream>>>(d_X, rows, (int)m, rp.D, d_cnt);
+        row_means_quad_kernel<false><<<(unsigned)g, BS_THREADS, 0, (cudaStream_t)stream>>>(d_X, rows, (int)m, rp.D, d_cnt, nullptr);
         return check_launch("row_means_quad_kernel");
     }
     int64_t groups_per_cta = RM_THREADS / 8;
@@ -470,6 +516,36 @@ extern "C" int omb_row_means(const double* d_X, int64_t rows, int64_t m, double*
     if (grid > cap) grid = cap;
     row_means_kernel<<<(unsigned)grid, RM_THREADS, 0, (cudaStream_t)stream>>>(d_X, rows, m, d_cnt);
     return check_launch("row_means_kernel");
+}
+
+static int center_given(const double* d_X, int64_t rows, int64_t m, const double* d_cnt, double* d_X0c, cudaStream_t st)
+{
+    int64_t g = ceil_div(rows * (m >> 1), 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    center_given_kernel<<<(unsigned)g, 256, 0, st>>>(d_X, rows, m, d_cnt, d_X0c);
+    return check_launch("center_given_kernel");
+}
+
+extern "C" int omb_center_rows(const double* d_X, int64_t rows, int64_t m, int compute_means, double* d_cnt,
+                               double* d_X0c, void* stream)
+{
+    OMB_CHECK_ARG(d_X && d_cnt && d_X0c, "null pointer");
+    OMB_CHECK_ARG(rows > 0 && m > 0 && (m & 1) == 0, "m must be positive and even");
+    OMB_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_X) | reinterpret_cast<uintptr_t>(d_X0c)) & 15) == 0, "X, X0c must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!compute_means) return center_given(d_X, rows, m, d_cnt, d_X0c, st);
+    const BlockPlan rp = make_plan(m);
+    if (m >= 32 && rp.D <= 3) {
+        int64_t g = ceil_div(ceil_div(rows, (int64_t)(8 >> rp.D)), BS_THREADS / 32);
+        const int64_t cap2 = (int64_t)sm_count() * 4;
+        if (g > cap2) g = cap2;
+        row_means_quad_kernel<true><<<(unsigned)g, BS_THREADS, 0, st>>>(d_X, rows, (int)m, rp.D, d_cnt, d_X0c);
+        return check_launch("row_means_quad_kernel");
+    }
+    int rc = omb_row_means(d_X, rows, m, d_cnt, stream);
+    if (rc) return rc;
+    return center_given(d_X, rows, m, d_cnt, d_X0c, st);
 }
 
 extern "C" int64_t omb_block_stats_ws_bytes(int64_t F, int64_t block_elems)

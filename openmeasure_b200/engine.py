@@ -47,6 +47,32 @@ def _ws(nbytes, device):
 
 TB = 128    # candidates per basis tile (OMB_TB in csrc/common.cuh)
 
+# One spare buffer per device for the centred copy of X that the many-snapshot tensor-core passes read: it is
+# as large as X itself (33 GB at config 3, 68.7 GB per GPU at config 5), lives from the Gram pass to the
+# back-projection, and is handed from fit to fit instead of going through the caching allocator each time
+# (splitting and re-growing a block of that size cost 100+ ms per fit).  release_scratch() returns it.
+_SCRATCH_POOL = {}
+
+
+def _scratch_take(dev, nbytes):
+    buf = _SCRATCH_POOL.get(dev)
+    if buf is not None and buf.numel() >= nbytes:
+        del _SCRATCH_POOL[dev]
+        return buf
+    return None
+
+
+def _scratch_give(dev, buf):
+    old = _SCRATCH_POOL.get(dev)
+    if old is None or old.numel() < buf.numel():
+        _SCRATCH_POOL[dev] = buf
+
+
+def release_scratch():
+    """Return the pooled centred-copy buffers to the allocator."""
+    _SCRATCH_POOL.clear()
+
+
 
 def tiles_for(n):
     return (int(n) + TB - 1) // TB
@@ -86,6 +112,50 @@ class Engine:
         self.vn = None
         self.r = None
         self.ntiles = tiles_for(self.n_loc)
+        self._X0c = None                                 # centred copy of X for the many-snapshot tensor-core passes
+
+    # ------------------------------------------------------------------------------------ centred copy
+    def _centred_copy_wanted(self):
+        """m > 64 (the DMMA-bound kernels), even m, aligned X, and room for a second copy of X next to the basis
+        and the placement workspace.  OMB_CENTRED_COPY=0 forces the in-kernel centring path."""
+        import os
+        if self.m <= 64 or (self.m & 1) or (self.X.data_ptr() & 15) or os.environ.get("OMB_CENTRED_COPY", "1") == "0":
+            return False
+        pooled = _SCRATCH_POOL.get(self.dev)
+        if pooled is not None and pooled.numel() >= 8 * self.n_loc * self.m:
+            return True
+        free, _ = torch.cuda.mem_get_info(self.dev)
+        free += torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
+        need = 8 * self.n_loc * self.m
+        return free - need >= 16 * self.n_loc * min(self.m, 128) + (1 << 30)
+
+    def _new_centred(self):
+        """Uninitialised buffer shaped like X from the scratch pool (or the allocator); None when out of memory."""
+        nbytes = 8 * self.n_loc * self.m
+        buf = _scratch_take(self.dev, nbytes)
+        if buf is None:
+            try:
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            except torch.OutOfMemoryError:
+                return None
+        self._X0c_buf = buf
+        return buf[:nbytes].view(torch.float64).view(self.n_loc, self.m)
+
+    def _drop_centred(self):
+        """The centred copy's last reader has been queued on the current stream: hand the buffer on."""
+        buf = getattr(self, "_X0c_buf", None)
+        if buf is not None:
+            _scratch_give(self.dev, buf)
+        self._X0c, self._X0c_buf = None, None
+
+    def _centre(self, X, cnt, compute_means, out=None):
+        """X0c = X - cnt (row means computed in the same pass when asked); None when there is no room."""
+        if out is None:
+            out = self._new_centred()
+            if out is None:
+                return None
+        _lib.call("omb_center_rows", _p(X), int(X.shape[0]), self.m, 1 if compute_means else 0, _p(cnt), _p(out), _stream())
+        return out
 
     def check_p2p(self):
         """Raise if a peer never answered during a peer-memory exchange since the last check (the pivot
@@ -149,9 +219,12 @@ class Engine:
             L = _lib.load()
             ws1 = _ws(L.omb_block_stats_ws_bytes(1, blk), self.dev)
             fuse_gram = defer_row_means and axis_cnt == 1
+            X0c = None
             if fuse_gram:
                 Gf = torch.empty(F * m * m, dtype=torch.float64, device=self.dev)
                 gws = _ws(L.omb_gram_ws_bytes(1, ncl, m), self.dev)
+                if self._centred_copy_wanted():
+                    X0c = self._new_centred()
             cur = torch.cuda.current_stream()
             for f in range(F):
                 cur.wait_event(arrival[f])
@@ -159,12 +232,17 @@ class Engine:
                 _lib.call("omb_block_stats", _p(Xf), 1, blk, 0, count, _p(sf), _p(ws1), st)
                 if scale_type in NEEDS_SQDEV and self.world == 1:
                     _lib.call("omb_block_stats", _p(Xf), 1, blk, 1, count, _p(sf), _p(ws1), st)
-                if fuse_gram:
+                if fuse_gram and X0c is not None:
+                    X0f = X0c[f * ncl:(f + 1) * ncl]
+                    self._centre(Xf, cf, True, out=X0f)
+                    _lib.call("omb_gram", _p(X0f), 1, ncl, m, None, _p(Gf[f * m * m:(f + 1) * m * m]), _p(gws), st)
+                elif fuse_gram:
                     _lib.call("omb_gram_rowmeans", _p(Xf), 1, ncl, m, _p(cf), _p(Gf[f * m * m:(f + 1) * m * m]), _p(gws), st)
                 elif axis_cnt == 1:
                     _lib.call("omb_row_means", _p(Xf), ncl, m, _p(cf), st)
             if fuse_gram:
                 self._Gf_cached = Gf
+                self._X0c = X0c
             if self.world > 1:
                 stats = self.comm.combine_stats(stats, F, sq=False)
                 if scale_type in NEEDS_SQDEV:
@@ -186,6 +264,8 @@ class Engine:
         scl = torch.empty(F, dtype=torch.float64, device=self.dev)
         _lib.call("omb_finalize_scale", _p(stats), F, count, SCALE_CODES[scale_type], _p(scl),
                   1 if axis_cnt is None else 0, _p(cnt), ncl, st)
+        if arrival is None:
+            self._drop_centred()                        # a copy left over from an earlier fit
         self.cnt, self.scl, self.block_stats = cnt, scl, stats
         self._cnt_pending = pending
         return cnt, scl
@@ -203,6 +283,13 @@ class Engine:
         ws = _ws(_lib.load().omb_gram_ws_bytes(F, ncl, m), self.dev)
         if centred and getattr(self, "_Gf_cached", None) is not None:   # produced block by block behind the H2D copy
             Gf, self._Gf_cached = self._Gf_cached, None
+        elif centred and self._centred_copy_wanted() and \
+                (X0c := self._centre(self.X, self._cnt, self._cnt_pending)) is not None:
+            # many snapshots: the row means (when still due) and a centred copy of X from one pass, then the
+            # tensor-core Gram on the copy -- no FP64 add left in its inner loop; back-projection reuses the copy
+            self._cnt_pending = False
+            self._X0c = X0c
+            _lib.call("omb_gram", _p(X0c), F, ncl, m, None, _p(Gf), _p(ws), st)
         elif centred and self._cnt_pending:             # row means + centred Grams from one read of X
             _lib.call("omb_gram_rowmeans", _p(self.X), F, ncl, m, _p(self._cnt), _p(Gf), _p(ws), st)
             self._cnt_pending = False
@@ -243,7 +330,10 @@ class Engine:
             V = SV[m:].view(m, m)
         S = SV[:m]
         Wfull = torch.empty(m, m, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_pod_weights", _p(w.contiguous()), _p(V), m, C.c_double(m * EPS), _p(S), _p(Wfull), _stream())
+        # a mode is "resolved" by the Gram route when lambda > m eps lambda_1, i.e. sigma > sqrt(m eps) sigma_1: below
+        # that the eigenvalue is rounding noise of G (a true null direction shows up as +-m eps lambda_1) and the
+        # mode gets a zero weight instead of noise amplified by 1/sigma (ROM._pod then takes the full-width route)
+        _lib.call("omb_pod_weights", _p(w.contiguous()), _p(V), m, C.c_double(float(np.sqrt(m * EPS))), _p(S), _p(Wfull), _stream())
         self.pod_weights, self.pod_sv = Wfull, SV
         return S, V
 
@@ -256,9 +346,12 @@ class Engine:
         assert m == self.m
         Ut = self._new_basis(r)
         vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev) if norms else None
-        _lib.call("omb_backproject", _p(self.X), self.F, self.n_c_loc, self.m,
-                  _p(self.cnt if centred else None), _p(self.scl if scaled else None), _p(W), r,
-                  _p(Ut), _p(vn), _stream())
+        src, cnt = self.X, (self.cnt if centred else None)
+        if centred and self._X0c is not None:           # the centred copy the Gram pass left behind
+            src, cnt = self._X0c, None
+        _lib.call("omb_backproject", _p(src), self.F, self.n_c_loc, self.m, _p(cnt), _p(self.scl if scaled else None),
+                  _p(W), r, _p(Ut), _p(vn), _stream())
+        self._drop_centred()                            # its last reader has been queued: the memory can be reused
         self.Ut, self.vn, self.r = Ut, vn, r
         return Ut
 
@@ -304,14 +397,17 @@ class Engine:
             H = self.comm.sum_ordered(H.contiguous())
         return H, U1
 
-    def basis_rotate(self, U1, M):
-        """Install U_r <- U1 M (M: r x r) as the basis, with fresh placement norms (the back-projection
-        kernel with U1 in the role of the snapshots)."""
-        r = self.r
+    def basis_rotate(self, U1, M, norms=True):
+        """Install U_r <- U1 M (U1: n_loc x k rows, M: k x r) as the basis, with fresh placement norms (the
+        back-projection kernel with U1 in the role of the snapshots)."""
+        M = M.contiguous()
+        k, r = (int(v) for v in M.shape)
+        assert int(U1.shape[1]) == k
+        self.Ut = None                                # U1 holds the data: the old tiles can go before the new ones come
         Ut = self._new_basis(r)
-        vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev)
-        _lib.call("omb_backproject", _p(U1), 1, self.n_loc, r, None, None, _p(M.contiguous()), r, _p(Ut), _p(vn), _stream())
-        self.Ut, self.vn = Ut, vn
+        vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev) if norms else None
+        _lib.call("omb_backproject", _p(U1), 1, self.n_loc, k, None, None, _p(M), r, _p(Ut), _p(vn), _stream())
+        self.Ut, self.vn, self.r = Ut, vn, r
 
     def mask_rows(self, mask_dev):
         """optimal_placement(mask=...): zero the excluded rows of the basis in place (:737-738)."""

@@ -353,21 +353,35 @@ class ROM:
             S_h = S.cpu().numpy()
             lam = S_h ** 2
             r = self._choose_rank(100 * np.cumsum(lam) / np.sum(lam), eng.m, select_modes, n_modes)
-        # modes whose singular value is numerically zero carry no information (row-centred data
-        # has rank m-1): eig_pod's weights V diag(1/sigma) hold a zero column for them
+        # modes the Gram route cannot resolve (sigma <= sqrt(m eps) sigma_1: their eigenvalue is rounding noise of
+        # G) get a zero weight in eig_pod; row-centred data always has one (rank m - 1)
         eng.backproject(eng.pod_weights[:, :r].contiguous(), centred=centred, scaled=scaled)
         sv_h = eng.pod_sv.cpu().numpy()                       # sigma | V in one D2H
-        S_h = sv_h[:eng.m].copy()
-        Vr_h = sv_h[eng.m:].reshape(eng.m, eng.m)[:, :r].copy()
-        # smallest retained singular value that carries information (the numerically-zero mode of
-        # row-centred data, back-projected with a zero weight, is excluded from the accuracy estimate)
-        live = S_h[:r][S_h[:r] > S_h[0] * (eng.m * _eng.EPS)]
+        eng.check_p2p()
+        m = eng.m
+        S_h = sv_h[:m].copy()
+        V_h = sv_h[m:].reshape(m, m).copy()
+        Vr_h = V_h[:, :r].copy()
+        floor = float(np.sqrt(m * _eng.EPS))
+        resolved = S_h > S_h[0] * floor
+        unresolved = int(np.count_nonzero(~resolved[:r]))
+        if centred and r == m and not resolved[m - 1]:
+            unresolved -= 1                                   # the structural null mode of row-centred data
+        live = S_h[:r][resolved[:r]]
         s_min = float(live[-1]) if live.size else float(S_h[0])
-        bound = float(_eng.EPS * (S_h[0] / s_min) ** 2) if s_min > 0 else 0.0
+        # Gram route: sigma_r to eps (sigma_1/sigma_r)^2.  Correction on the r retained modes: eps sigma_1/sigma_r,
+        # valid while the subspace itself is good, (eps (sigma_1/sigma_r)^2)^2 small.  Beyond that the Gram of X0
+        # does not even contain the small modes: full-width route.
+        b0 = float(_eng.EPS * (S_h[0] / s_min) ** 2) if s_min > 0 else 0.0
+        bound = b0
         self.pod_refined = False
-        if self.pod_refine is True or (self.pod_refine == 'auto' and bound > self.pod_refine_tol):
-            # The Gram route loses eps (sigma_1/sigma_r)^2.  One CholeskyQR2-style correction on the
-            # basis itself brings that down to eps sigma_1/sigma_r:  U1 = X0 V_r S^-1 = P S1 Q^T
+        want = self.pod_refine
+        if want == 'full' or (want in ('auto', True) and (unresolved > 0 or max(b0 * b0, _eng.EPS * S_h[0] / s_min) > 1e-10)
+                              and (want is True or b0 > self.pod_refine_tol)):
+            S_h, Vr_h, bound = self._pod_full_width(eng, S_h, V_h, r, centred, scaled)
+            self.pod_refined = 'full'
+        elif want is True or (want == 'auto' and b0 > self.pod_refine_tol):
+            # One CholeskyQR2-style correction on the basis itself:  U1 = X0 V_r S^-1 = P S1 Q^T
             # (from H = U1^T U1 = Q S1^2 Q^T);  X0 V_r = P (S1 Q^T S) = P B;  SVD B = A1 S2 A2^T  =>
             # U = U1 (Q S1^-1 A1),  sigma = S2,  V = V_r A2.  Two extra passes over the n x r basis.
             H, U1 = eng.basis_gram()
@@ -383,8 +397,8 @@ class ROM:
             Vr_h, M = Vn * sgn, M * sgn
             eng.basis_rotate(U1, torch.from_numpy(np.ascontiguousarray(M)).to(eng.dev))
             S_h[:r] = S2
-            live = S2[S2 > S2[0] * (eng.m * _eng.EPS)]
-            bound = float(_eng.EPS * S2[0] / live[-1]) if live.size else 0.0
+            live = S2[S2 > S2[0] * floor]
+            bound = float(max(_eng.EPS * S2[0] / live[-1], b0 * b0)) if live.size else 0.0
             self.pod_refined = True
         lam = S_h ** 2
         exp_variance = 100 * np.cumsum(lam) / np.sum(lam)     # :274-275

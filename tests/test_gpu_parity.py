@@ -419,6 +419,43 @@ def test_multirank_matches_single_rank(torch_cuda, cells, block):
     np.testing.assert_allclose(full, one["rec"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("cells,m,r", [([300, 260], 130, 40), ([200, 180, 190], 256, 64), ([333, 300], 256, 100)])
+def test_multirank_many_snapshots(torch_cuda, cells, m, r):
+    """m > 64: the many-snapshot Gram / back-projection kernels and the library eigensolver whose result rank 0
+    broadcasts (engine.eig_pod) -- the branch configs[2] and configs[4] take on more than one GPU."""
+    from oracle import pod_oracle as po, synth as osynth
+    F = 2
+    n_c = sum(cells)
+    X = osynth.snapshots(F, n_c, m, r)
+    ref = po.placement_pipeline(X, F, r)
+    one = _run_ranks(torch_cuda, X, F, [n_c], r, 8)[0]
+    np.testing.assert_array_equal(one["piv"], ref["piv"])
+    np.testing.assert_allclose(one["S"], ref["Sigma_r"], rtol=RTOL)
+    full = np.zeros((F * n_c, 1))
+    for o in _run_ranks(torch_cuda, X, F, cells, r, 8):
+        np.testing.assert_array_equal(o["piv"], ref["piv"])
+        np.testing.assert_allclose(o["S"], one["S"], rtol=1e-12)             # G-invariance of sigma
+        np.testing.assert_allclose(np.abs(o["Theta"]), np.abs(one["Theta"]), rtol=0, atol=1e-10)
+        full[o["rows"]] = o["rec"]
+    np.testing.assert_allclose(full, one["rec"], rtol=1e-9)
+
+
+def test_two_gpu_peer_memory_parity(torch_cuda):
+    """Real NVLink peers (needs >= 2 GPUs; the driver's 1-GPU run skips it): torchrun tools/mr_check.py -- the
+    peer-memory all-gather / all-reduce kernels and the in-kernel pivot exchange against the single-GPU run."""
+    import os, subprocess, sys
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in (["20000", "41", "40"], ["6000", "256", "100"]):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533",
+                              os.path.join(root, "tools", "mr_check.py")] + extra,
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert "-> OK" in out.stdout
+
+
 # ---------------------------------------------------------------------------------------------
 # S3: one-CTA Jacobi eigensolver vs LAPACK (np.linalg.eigh), including the rank-deficient Gram of
 # row-centred data (sigma_m ~ 0) and graded spectra
@@ -739,3 +776,110 @@ def test_api_extras_match_reference_golden(torch_cuda):
     np.testing.assert_array_equal(spr.scl_vector, z["scl_vector"])
     np.testing.assert_allclose(spr.reconstruct(Ar_p, sampling=z["S"]), z["X_rec_s"], rtol=1e-10)
     np.testing.assert_allclose(spr.unscale_data(z["x0"], sampling=z["S"]), z["x_uns"], rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------
+# streamed reconstruct (configs[3]: the n x N result never exists on the device): row chunks through the
+# two-buffer ring must equal the one-shot result bit for bit, for every `out` form
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_c,r,N,chunk", [(700, 10, 7, 128), (1100, 16, 16, 256), (3001, 40, 130, 1024), (900, 14, 258, 384)])
+def test_reconstruct_streams_in_row_chunks(torch_cuda, n_c, r, N, chunk):
+    from oracle import pod_oracle as po, synth as osynth
+    F, m = 3, max(24, r + 8)
+    X = osynth.snapshots(F, n_c, m, r)
+    ref = po.fit(X, F, "std", 1, "number", r)
+    spr = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    spr.fit(select_modes='number', n_modes=r)
+    rng = np.random.default_rng(N)
+    A = rng.standard_normal((N, r))
+    whole = spr.reconstruct(A, chunk_rows=1 << 30)                      # one chunk
+    Ur, sg = _sign_align(spr.Ur, ref["Ur"])
+    np.testing.assert_allclose(Ur, ref["Ur"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(whole, po.reconstruct(ref["Ur"], A * sg, ref["X_cnt"], ref["X_scl"]), rtol=1e-9, atol=1e-9)
+    np.testing.assert_array_equal(spr.reconstruct(A, chunk_rows=chunk), whole)
+    buf = np.full((F * n_c, N), np.nan)
+    assert spr.reconstruct(A, out=buf, chunk_rows=chunk) is buf
+    np.testing.assert_array_equal(buf, whole)
+    seen = []
+    got = np.empty_like(whole)
+
+    def sink(row0, block):
+        seen.append((row0, block.shape[0]))
+        got[row0:row0 + block.shape[0]] = block
+
+    assert spr.reconstruct(A, out=sink, chunk_rows=chunk) is None
+    np.testing.assert_array_equal(got, whole)
+    assert [s0 for s0, _ in seen] == list(range(0, F * n_c, chunk)) and sum(k for _, k in seen) == F * n_c
+    blocks = [(r0, b.copy()) for r0, b in spr.reconstruct_chunks(A[:1], chunk_rows=chunk)]
+    np.testing.assert_array_equal(np.vstack([b for _, b in blocks]), whole[:, :1])
+    with pytest.raises(ValueError):
+        spr.reconstruct(A, out=np.empty((3, 3)))
+
+
+def test_from_host_shard_matches_constructor(torch_cuda):
+    """SPR.from_host (one rank's pinned host shard, block-wise upload overlapped with the first passes) against
+    the plain constructor on the same matrix."""
+    torch = torch_cuda
+    from oracle import synth as osynth
+    F, n_c, m, r = 4, 2500, 41, 12
+    X = osynth.snapshots(F, n_c, m, r)
+    Xp = torch.from_numpy(X).pin_memory().numpy()
+    a = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    b = _sps().SPR.from_host(Xp, F, np.zeros((n_c, 3)), group=False)
+    for s in (a, b):
+        s.fit(select_modes='number', n_modes=r)
+        s.optimal_placement()
+    np.testing.assert_array_equal(a.X_cnt, b.X_cnt)
+    np.testing.assert_array_equal(a.X_scl, b.X_scl)
+    np.testing.assert_allclose(a.Sigma_r, b.Sigma_r, rtol=1e-13)
+    np.testing.assert_array_equal(a.qr_pivots, b.qr_pivots)
+    with pytest.raises(TypeError):
+        _sps().SPR.from_host(torch.from_numpy(X), F)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE shapes: configs[0] (README 2D ROM: 9 x 18 362 x 41, r = 14) end to end against the oracle, and
+# configs[1] pivots against LAPACK run on the GPU's own basis
+# ---------------------------------------------------------------------------------------------
+def test_config1_shape_full_pipeline_matches_oracle(torch_cuda):
+    from oracle import pod_oracle as po, synth as osynth
+    F, n_c, m, r = 9, 18362, 41, 14
+    X = osynth.snapshots(F, n_c, m, r)
+    ref = po.placement_pipeline(X, F, r)
+    spr = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    spr.fit(select_modes='number', n_modes=r)
+    C = spr.optimal_placement()
+    np.testing.assert_array_equal(spr.X_cnt, ref["X_cnt"])
+    np.testing.assert_array_equal(spr.X_scl, ref["X_scl"])
+    np.testing.assert_allclose(spr.Sigma_r, ref["Sigma_r"], rtol=RTOL)
+    Ur, sg = _sign_align(spr.Ur, ref["Ur"])
+    np.testing.assert_allclose(Ur, ref["Ur"], rtol=0, atol=1e-10)
+    np.testing.assert_array_equal(spr.qr_pivots, ref["piv"])
+    spr.train(C)
+    Co = po.one_hot(ref["piv"], X.shape[0])
+    Th = po.theta(Co, ref["Ur"])
+    np.testing.assert_allclose(spr.Theta * sg, Th, rtol=0, atol=1e-10)
+    ys = []
+    for j in (0, 7, 40):
+        y = np.zeros((r, 3))
+        y[:, 0] = X[ref["piv"], j]
+        y[:, 2] = ref["piv"] // n_c
+        ys.append(y)
+    a, _ = spr.predict(ys)
+    ao, _ = po.predict_ols(Th, ys, Co, ref["X_cnt"], ref["X_scl"], n_c)
+    np.testing.assert_allclose(a * sg, ao, rtol=1e-9, atol=1e-9 * np.abs(ao).max())
+    np.testing.assert_allclose(spr.reconstruct(a), po.reconstruct(ref["Ur"], ao, ref["X_cnt"], ref["X_scl"]), rtol=RTOL)
+
+
+def test_config2_shape_pivots_match_lapack_on_device_basis(torch_cuda):
+    """configs[1] (1 652 580 x 41, r = 40): the blocked GPU placement against scipy.linalg.qr(pivoting=True) run on
+    the basis the GPU produced (the reference's own call, sparse_sensing.py:739; ~10 s of LAPACK)."""
+    torch = torch_cuda
+    from openmeasure_b200 import synth as gsynth
+    F, n_c, m, r = 9, 183620, 41, 40
+    spr = _sps().SPR.from_device(gsynth.snapshots(F, n_c, m, r), F, group=False)
+    spr.fit(select_modes='number', n_modes=r)
+    spr.optimal_placement()
+    Ur = spr.Ur
+    _, _, P = sla.qr(Ur.T, pivoting=True, mode='economic')
+    np.testing.assert_array_equal(spr.qr_pivots, P[:r])

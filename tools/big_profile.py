@@ -25,6 +25,16 @@ for rep in range(reps):
     eng.backproject(eng.pod_weights[:, :r].contiguous())
     t[4].record()
     torch.cuda.synchronize()
+g = [ev(), ev(), ev()]
+for rep in range(reps):
+    g[0].record()
+    eng.gram(centred=False, scaled=False)
+    g[1].record()
+    eng.cnt.zero_()
+    eng.cnt
+    g[2].record()
+    torch.cuda.synchronize()
+print(f"gram uncentred (no row means, no centring)  {g[0].elapsed_time(g[1]):9.3f} ms  {n * m * (m + 1.0) / g[0].elapsed_time(g[1]) / 1e9:8.2f} TFLOP/s algorithmic")
 A = torch.rand(N, r, dtype=torch.float64, device="cuda")
 rows = min(n, (1 << 30) // (8 * N) // 128 * 128)
 out = torch.empty(rows, N, dtype=torch.float64, device="cuda")

@@ -12,8 +12,10 @@ from openmeasure_b200.sparse_sensing import SPR
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-F, m, r = 9, 41, 40
 n_c_loc = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 41
+r = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+F = 9 if m != 1024 else 8
 n_c = n_c_loc * world
 Xl = synth.snapshots(F, n_c, m, r, cell0=rank * n_c_loc, ncell_loc=n_c_loc)
 spr = SPR.from_device(Xl, F, group=None)
@@ -32,7 +34,7 @@ if rank == 0:
     ds = float(np.max(np.abs(spr.Sigma_r - one.Sigma_r) / one.Sigma_r))
     dth = float(np.max(np.abs(np.abs(spr.Theta) - np.abs(one.Theta))))
     ok = same_piv and ds < 1e-12 and dth < 1e-9
-    print(f"world={world} rows={F*n_c} exchange={spr._eng.qr_exchange} p2p_allgathers={getattr(spr._eng.comm, 'p2p_collectives', 0)} "
+    print(f"world={world} rows={F*n_c} m={m} r={r} exchange={spr._eng.qr_exchange} p2p_allgathers={getattr(spr._eng.comm, 'p2p_collectives', 0)} "
           f"pivots_identical={same_piv} max_rel_dsigma={ds:.2e} max_dTheta={dth:.2e} min_gap={spr.qr_gap.min():.2e} -> {'OK' if ok else 'FAIL'}",
           flush=True)
 dist.barrier()
