@@ -119,7 +119,10 @@ class ROM:
 
     # POD accuracy control (extension): the Gram route resolves sigma_r to eps (sigma_1/sigma_r)^2;
     # when that estimate exceeds pod_refine_tol a CholeskyQR2-style correction of the basis (two
-    # more passes over the n x r modes) brings it to eps sigma_1/sigma_r.  'auto' | True | False.
+    # more passes over the n x r modes) brings it to eps sigma_1/sigma_r; when even that is not
+    # enough (sigma_r/sigma_1 < ~1e-5, or a retained mode below sqrt(m eps) sigma_1 that the Gram
+    # matrix cannot hold at all) the full-width route (_pod_full_width: the accuracy class of a TSQR)
+    # runs.  'auto' | True (always correct) | 'full' (always full width) | False.
     pod_refine = 'auto'
     pod_refine_tol = 1e-11
 
@@ -376,8 +379,8 @@ class ROM:
         bound = b0
         self.pod_refined = False
         want = self.pod_refine
-        if want == 'full' or (want in ('auto', True) and (unresolved > 0 or max(b0 * b0, _eng.EPS * S_h[0] / s_min) > 1e-10)
-                              and (want is True or b0 > self.pod_refine_tol)):
+        if want == 'full' or (want in ('auto', True) and (
+                unresolved > 0 or (b0 > self.pod_refine_tol and max(b0 * b0, _eng.EPS * S_h[0] / s_min) > 1e-10))):
             S_h, Vr_h, bound = self._pod_full_width(eng, S_h, V_h, r, centred, scaled)
             self.pod_refined = 'full'
         elif want is True or (want == 'auto' and b0 > self.pod_refine_tol):
@@ -411,7 +414,63 @@ class ROM:
             import warnings
             warnings.warn("POD: estimated relative error of the smallest retained singular value is %.1e "
                           "(sigma_r/sigma_1 = %.1e)" % (bound, S_h[r - 1] / S_h[0]), RuntimeWarning)
+        elif self.pod_refined == 'full' and S_h[r - 1] < 1e-6 * S_h[0]:
+            # not a defect of this path: ANY backward-stable SVD (LAPACK's included) carries eps sigma_1/sigma_r
+            self.pod_rel_err_vs_backward_stable = float(50 * _eng.EPS * S_h[0] / max(S_h[r - 1], 1e-300))
         return Ar, exp_variance[:r]
+
+    def _pod_full_width(self, eng, S_h, V_h, r, centred, scaled):
+        """POD of a matrix whose retained singular values reach below what a Gram matrix can hold
+        (sigma_r/sigma_1 < ~1e-5: lambda_r/lambda_1 is at or under the rounding level of G).  The accuracy
+        class of a Householder/TSQR route from Gram-kernel passes only (shifted-CholeskyQR3 style, with
+        eigen-decompositions in place of Cholesky factors because row-centred X0 is exactly rank deficient):
+
+            X0 = Y C,   Y_0 = X0 V S_f^-1,  C_0 = S_f V^T       (S_f = sigma floored at sqrt(m eps) sigma_1: exact
+                                                                 identity for ANY orthogonal V, however inaccurate)
+            H = Y^T Y = Q S1^2 Q^T  ->  Y <- Y Q S1_f^-1,  C <- S1_f Q^T C       (cond(Y) ~ 1e7 -> ~1e2 -> ~1)
+            cond(Y) small:  SVD C = A1 S2 A2^T  =>  U = Y A1[:, :r],  sigma = S2,  V = A2
+
+        All m columns are carried (n x m basis passes, two or three of them) -- only this hard case pays.
+        Returns (sigma (m,), V_r (m, r), bound)."""
+        m = eng.m
+        floor = float(np.sqrt(m * _eng.EPS))
+        Sf = np.maximum(S_h, floor * S_h[0])
+        Cm = Sf[:, None] * V_h.T
+        dev = eng.dev
+        eng.backproject(torch.from_numpy(np.ascontiguousarray(V_h / Sf[None, :])).to(dev), centred=centred, scaled=scaled,
+                        norms=False)
+        cond = np.inf
+        for it in range(4):
+            H, Y = eng.basis_gram()
+            lam, Q = np.linalg.eigh(H.cpu().numpy())
+            lam, Q = lam[::-1], Q[:, ::-1]
+            S1 = np.sqrt(np.maximum(lam, 0.0))
+            S1f = np.maximum(S1, floor * S1[0])
+            res = S1 > floor * S1[0]
+            if centred and not res[-1]:
+                res[-1] = True                                # the structural null direction stays tiny: not a defect
+                cond_vals = S1[:-1][res[:-1]]
+            else:
+                cond_vals = S1[res]
+            unresolved = int(np.count_nonzero(~res))
+            cond = float(cond_vals[0] / cond_vals[-1]) if cond_vals.size else 1.0
+            B = (S1f[:, None] * Q.T) @ Cm
+            T = Q / S1f[None, :]
+            if (unresolved == 0 and cond * cond * _eng.EPS < 1e-13) or it == 3:
+                A1, S2, A2t = np.linalg.svd(B)
+                Vn = A2t.T[:, :r]
+                sgn = np.sign(Vn[np.argmax(np.abs(Vn), axis=0), np.arange(r)])
+                sgn[sgn == 0] = 1.0
+                M = (T @ A1[:, :r]) * sgn
+                eng.basis_rotate(Y, torch.from_numpy(np.ascontiguousarray(M)).to(dev))
+                self.pod_passes = it + 1
+                bound = float(max(cond * cond * _eng.EPS, m * _eng.EPS))
+                if unresolved:
+                    bound = 1.0
+                return S2.copy(), Vn * sgn, bound
+            eng.basis_rotate(Y, torch.from_numpy(np.ascontiguousarray(T)).to(dev), norms=False)
+            Cm = B
+            del Y
 
     def decomposition(self, X0, select_modes='variance', n_modes=99):
         """POD of a scaled matrix X0 (n, m): returns (Ur, Ar, exp_variance[:r])
@@ -450,7 +509,7 @@ class ROM:
         self.r = Ar.shape[1]
         sig = np.linalg.norm(Ar, axis=0)                  # :504-507 (m x r, host-trivial)
         self.Sigma_r = sig
-        self.Vr = Ar / sig
+        self.Vr = Ar / np.where(sig > 0, sig, 1.0)        # an exactly-zero mode (dropped null direction) stays zero
 
     # ------------------------------------------------------------------ reconstruct (a11)
     def reconstruct(self, Ar, sampling=None, *, out=None, chunk_rows=None):

@@ -711,6 +711,57 @@ def test_pod_refinement_graded_spectrum(torch_cuda, n, m, r):
     np.testing.assert_allclose(Ur @ Ar.T, (Uref[:, :r] * Sref[:r]) @ Vtref[:r], atol=1e-10 * Sref[0])
 
 
+@pytest.mark.parametrize("n,m,r,lo", [(6000, 16, 12, -6.0), (5000, 40, 30, -7.0), (4000, 96, 40, -7.0), (3000, 130, 60, -9.0)])
+def test_pod_hard_spectrum_full_width_route(torch_cuda, n, m, r, lo):
+    """sigma_r / sigma_1 = 1e-6 ... 1e-9 (SURVEY 8d's "hard" distribution): the Gram of X0 no longer holds the small
+    modes (lambda_r/lambda_1 <= eps), the one-pass correction is not enough either; the full-width route must agree
+    with the constructed spectrum and with np.linalg.svd (the reference's call, sparse_sensing.py:272) to 1e-10
+    relative or to the eps * sigma_1 absolute accuracy ANY backward-stable SVD has -- and say so without a warning.
+    With the correction switched off the same input must raise the accuracy warning."""
+    import warnings
+    sps = _sps()
+    rng = np.random.default_rng(n + m)
+    Uo, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    Vo, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    sig = np.concatenate([np.logspace(0, lo, r), np.logspace(lo - 0.5, lo - 2, m - r)])
+    X0 = (Uo * sig) @ Vo.T
+    Uref, Sref, Vtref = np.linalg.svd(X0, full_matrices=False)
+    tol = np.maximum(1e-10 * sig[:r], 200 * np.finfo(float).eps * sig[0])
+    rom = sps.ROM(X0, 1, None)
+    with warnings.catch_warnings():
+        warnings.filterwarnings("error", message="POD: estimated")
+        Ur, Ar, ev = rom.decomposition(X0, 'number', r)
+    assert rom.pod_refined == 'full' and rom.pod_rel_err_bound < 1e-10
+    S = np.linalg.norm(Ar, axis=0)
+    assert np.all(np.abs(S - sig[:r]) <= tol), np.max(np.abs(S - sig[:r]) / sig[:r])
+    assert np.all(np.abs(S - Sref[:r]) <= tol)
+    np.testing.assert_allclose(Ur.T @ Ur, np.eye(r), atol=1e-11)
+    # the factorisation itself: U diag(sigma) V^T reproduces the retained part of X0 to eps * sigma_1
+    np.testing.assert_allclose(Ur @ Ar.T, (Uref[:, :r] * Sref[:r]) @ Vtref[:r], atol=2e-13 * sig[0])
+    Ua, _ = _sign_align(Ur, Uref[:, :r])
+    np.testing.assert_allclose(Ua[:, : r // 3], Uref[:, : r // 3], atol=1e-9)
+    rom.pod_refine = False
+    with pytest.warns(RuntimeWarning, match="estimated relative error"):
+        rom.decomposition(X0, 'number', r)
+
+
+def test_pod_null_mode_of_centred_data_is_dropped_not_amplified(torch_cuda):
+    """r = m on row-centred data: the structural null mode (sigma_m = 0 up to rounding) gets a zero weight -- a
+    zero basis column, not rounding noise divided by ~1e-8 -- and does not trigger the full-width route."""
+    import warnings
+    from oracle import synth as osynth
+    F, n_c, m = 3, 1500, 24
+    X = osynth.snapshots(F, n_c, m, 16)
+    spr = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    with warnings.catch_warnings():
+        warnings.filterwarnings("error", message="POD: estimated")
+        spr.fit(select_modes='number', n_modes=m)
+    assert spr.pod_refined != 'full'
+    U = spr.Ur
+    assert np.abs(U[:, m - 1]).max() < 1e-6 and spr.Sigma_r[-1] < 1e-7 * spr.Sigma_r[0]
+    np.testing.assert_allclose(U[:, :m - 1].T @ U[:, :m - 1], np.eye(m - 1), atol=1e-9)
+
+
 # ---------------------------------------------------------------------------------------------
 # batched reconstruct across the kernel-selection boundary (TMA-pipelined 128 x 128 tiles for even
 # r / N, staged 64 x 64 tiles otherwise), ragged row and vector counts
