@@ -202,24 +202,41 @@ ols_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, int6
 }
 
 // ---------------------------------------------------------------------------------------------
-// Reconstruct, TMA-pipelined (even r, even N, row range aligned to basis tiles): persistent CTAs
-// walk 128 x 128 output tiles (one basis tile of candidates x 128 coefficient vectors).  A 32-mode
+// Reconstruct, warp-specialised and TMA-fed (even r, even N, row range aligned to basis tiles): persistent
+// CTAs walk 128 x 128 output tiles (one basis tile of candidates x 128 coefficient vectors).  A 32-mode
 // K-chunk of the basis tile is 32 contiguous 1 KB rows of the tiled layout (one bulk copy each, pitch
 // 132 doubles), the matching chunk of the coefficient rows 128 copies of 256 bytes (pitch 36): both
-// operands land bank-conflict free.  3-stage ring, every warp issues its share two chunks ahead and
-// across tile boundaries; 8 warps own 32 x 64 outputs each (64 DMMA accumulators per lane); the
-// epilogue scl * acc + cnt (two roundings, like the reference's multiply-then-add) goes out as
-// 16-byte stores.  FP64-tensor bound: 2 n r N flop against 8 n N written bytes (r/4 flop per byte).
+// operands land bank-conflict free.  The four warps of a producer warpgroup issue the copies of a chunk
+// (a bulk copy is a warp-serialised instruction of ~60 cycles: one warp cannot feed the ring) and hand
+// their registers to the 8 MMA warps (setmaxnreg), which own 32 x 64 outputs each (64 DMMA accumulators
+// per lane, double-buffered fragments) and run LDS + DMMA only; the first fragments of the next chunk are
+// loaded during the last k-step of the current one.  Epilogue scl * acc + cnt (two roundings, like the
+// reference's multiply-then-add) as 16-byte stores.  FP64-tensor bound: 2 n r N flop against 8 n N
+// written bytes (r/4 flop per byte).
 // ---------------------------------------------------------------------------------------------
 constexpr int RB_K = 32;
 constexpr int RB_LDA = OMB_TB + 4;          // [k][i]: == 4 (mod 16)
 constexpr int RB_LDB = RB_K + 4;            // [j][k]: == 4 (mod 16)
 constexpr int RB_STAGES = 3;
-constexpr int RB_THREADS = 256;
+constexpr int RB_MMA_WARPS = 8;
+constexpr int RB_THREADS = (RB_MMA_WARPS + 4) * 32;
 constexpr int RB_STAGE = RB_K * RB_LDA + OMB_TB * RB_LDB;
 static size_t reconstruct_big_smem() { return sizeof(double) * (size_t)RB_STAGES * RB_STAGE; }
 
-__global__ void __launch_bounds__(RB_THREADS)
+struct RbFrag { double a[4], b[8]; };
+
+__device__ __forceinline__ void rb_load(RbFrag& f, const double* sA, const double* sB, int k4, int fr, int fc, int ib, int jb)
+{
+    const int kk = k4 * 4 + fr;
+    const double* ra = sA + kk * RB_LDA + ib + fc;
+    const double* rb = sB + (jb + fc) * RB_LDB + kk;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) f.a[p] = ra[8 * p];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f.b[q] = rb[8 * q * RB_LDB];
+}
+
+__global__ void __launch_bounds__(RB_THREADS, 1)
 reconstruct_big_kernel(const double* __restrict__ Ut, int r, const double* __restrict__ Ac, int64_t N,
                        const double* __restrict__ cnt, const double* __restrict__ scl, int64_t n_c, int64_t row0,
                        int64_t nrows, double* __restrict__ out)
@@ -234,47 +251,55 @@ reconstruct_big_kernel(const double* __restrict__ Ut, int r, const double* __res
 
     for (int e = threadIdx.x; e < RB_STAGES * RB_STAGE; e += RB_THREADS) smem[e] = 0.0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < RB_STAGES; ++s) { mbar_init(&full_bar[s], RB_THREADS / 32); mbar_init(&empty_bar[s], RB_THREADS / 32); }
+        for (int s = 0; s < RB_STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], RB_MMA_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
     __syncthreads();
 
-    // ---- issue side: this warp's share (4 mode rows of the basis tile, 16 coefficient rows) of chunk gi
-    int64_t it_tile = blockIdx.x, gi = 0;
-    int it_c = 0;
-    auto issue = [&]() {
-        if (it_tile >= ntiles) return;
-        const int s = (int)(gi % RB_STAGES);
-        if (gi >= RB_STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((gi / RB_STAGES) - 1) & 1));
-        const int64_t ti = it_tile / tiles_j, tj = it_tile - ti * tiles_j;
-        const int k0 = it_c * RB_K;
-        const int kv = (r - k0) < RB_K ? (r - k0) : RB_K;
-        const int64_t j0 = tj * OMB_TB;
-        const int jv = (int)((N - j0) < OMB_TB ? (N - j0) : OMB_TB);
-        int na = kv - 4 * warp; na = na < 0 ? 0 : (na > 4 ? 4 : na);
-        int nb = jv - 16 * warp; nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-        double* sA = smem + (size_t)s * RB_STAGE;
-        double* sB = sA + RB_K * RB_LDA;
-        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(((int64_t)na * OMB_TB + (int64_t)nb * kv) * sizeof(double)));
-        __syncwarp();
-        if (lane < na) {
-            const int kk = 4 * warp + lane;
-            tma_load_bulk(sA + kk * RB_LDA, Ut + (tile0 + ti) * ((int64_t)r * OMB_TB) + (int64_t)(k0 + kk) * OMB_TB,
-                          OMB_TB * sizeof(double), &full_bar[s]);
-        } else if (lane >= 16 && lane - 16 < nb) {
-            const int jj = 16 * warp + lane - 16;
-            tma_load_bulk(sB + jj * RB_LDB, Ac + (j0 + jj) * r + k0, (uint32_t)(kv * sizeof(double)), &full_bar[s]);
+    if (warp >= RB_MMA_WARPS) {
+        // =========================== producer warpgroup: warp p copies mode rows [8p, 8p + 8) of the basis
+        // chunk and coefficient rows [32p, 32p + 32) ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int pw = warp - RB_MMA_WARPS;
+        int s = 0;
+        uint32_t ph = 0;
+        bool wrapped = false;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t ti = tile / tiles_j, tj = tile - ti * tiles_j;
+            const int64_t j0 = tj * OMB_TB;
+            const int jv = (int)((N - j0) < OMB_TB ? (N - j0) : OMB_TB);
+            int nb = jv - 32 * pw; nb = nb < 0 ? 0 : (nb > 32 ? 32 : nb);
+            const double* tb = Ut + (tile0 + ti) * ((int64_t)r * OMB_TB);
+            for (int c = 0; c < nch; ++c) {
+                if (wrapped) mbar_wait(&empty_bar[s], ph ^ 1);
+                const int k0 = c * RB_K;
+                const int kv = (r - k0) < RB_K ? (r - k0) : RB_K;
+                int na = kv - 8 * pw; na = na < 0 ? 0 : (na > 8 ? 8 : na);
+                double* sA = smem + (size_t)s * RB_STAGE;
+                double* sB = sA + RB_K * RB_LDA;
+                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(((int64_t)na * OMB_TB + (int64_t)nb * kv) * sizeof(double)));
+                __syncwarp();
+                if (lane < na) {
+                    const int kk = 8 * pw + lane;
+                    tma_load_bulk(sA + kk * RB_LDA, tb + (int64_t)(k0 + kk) * OMB_TB, OMB_TB * sizeof(double), &full_bar[s]);
+                }
+                if (lane < nb) {
+                    const int jj = 32 * pw + lane;
+                    tma_load_bulk(sB + jj * RB_LDB, Ac + (j0 + jj) * r + k0, (uint32_t)(kv * sizeof(double)), &full_bar[s]);
+                }
+                if (++s == RB_STAGES) { s = 0; ph ^= 1; wrapped = true; }
+            }
         }
-        ++gi;
-        if (++it_c == nch) { it_c = 0; it_tile += gridDim.x; }
-    };
-#pragma unroll 1
-    for (int u = 0; u < RB_STAGES - 1; ++u) issue();
+        return;
+    }
 
+    // =============================== MMA warps ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int fr = lane & 3, fc = lane >> 2;
     const int ib = (warp >> 1) * 32, jb = (warp & 1) * 64;
-    int64_t g = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t ti = tile / tiles_j, tj = tile - ti * tiles_j;
         double acc[4][8][2];
@@ -282,32 +307,39 @@ reconstruct_big_kernel(const double* __restrict__ Ut, int r, const double* __res
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[p][q][0] = acc[p][q][1] = 0.0;
+        RbFrag f[2];
+        mbar_wait(&full_bar[s], ph);
+        rb_load(f[0], smem + (size_t)s * RB_STAGE, smem + (size_t)s * RB_STAGE + RB_K * RB_LDA, 0, fr, fc, ib, jb);
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c, ++g) {
-            issue();
-            const int s = (int)(g % RB_STAGES);
-            mbar_wait(&full_bar[s], (uint32_t)((g / RB_STAGES) & 1));
+        for (int c = 0; c < nch; ++c) {
             const double* sA = smem + (size_t)s * RB_STAGE;
             const double* sB = sA + RB_K * RB_LDA;
+            const int s0 = s;
+            const bool more = c + 1 < nch;
             const int kv = (r - c * RB_K) < RB_K ? (r - c * RB_K) : RB_K;
+            if (++s == RB_STAGES) { s = 0; ph ^= 1; }
 #pragma unroll
             for (int k4 = 0; k4 < RB_K / 4; ++k4) {
-                const int kk = k4 * 4 + fr;
-                const bool kok = kk < kv;                      // stale modes of a ragged last chunk
-                double a[4], b[8];
+                if (k4 + 1 < RB_K / 4) rb_load(f[(k4 + 1) & 1], sA, sB, k4 + 1, fr, fc, ib, jb);
+                else if (more) {
+                    mbar_wait(&full_bar[s], ph);
+                    rb_load(f[0], smem + (size_t)s * RB_STAGE, smem + (size_t)s * RB_STAGE + RB_K * RB_LDA, 0, fr, fc, ib, jb);
+                }
+                RbFrag& g = f[k4 & 1];
+                if (k4 * 4 + 3 >= kv) {                        // ragged last chunk: modes kv.. hold stale data
+                    const bool kok = (k4 * 4 + fr) < kv;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) a[p] = sA[kk * RB_LDA + ib + 8 * p + fc];
+                    for (int p = 0; p < 4; ++p) g.a[p] = kok ? g.a[p] : 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) b[q] = sB[(jb + 8 * q + fc) * RB_LDB + kk];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) a[p] = kok ? a[p] : 0.0;
+                    for (int q = 0; q < 8; ++q) g.b[q] = kok ? g.b[q] : 0.0;
+                }
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) dmma884(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+                    for (int q = 0; q < 8; ++q) dmma884(acc[p][q][0], acc[p][q][1], g.a[p], g.b[q]);
             }
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s0])) : "memory");
         }
         // epilogue: x = scl * acc + cnt, 16-byte stores (N even, j even)
 #pragma unroll
