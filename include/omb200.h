@@ -205,6 +205,31 @@ int omb_gem_step(const double* d_Ut, int64_t n, int64_t r, double coef, int64_t 
                  int64_t* d_idx, double* d_val, double* d_row, void* stream);
 int omb_gem_exclude(const double* d_xyz, int64_t n_c, int64_t n, const int64_t* d_sensor, double d_min,
                     unsigned char* d_alive, void* stream);
+/* the same exclusion around a point given by its coordinates (row-sharded runs: the chosen cell may be a peer's) */
+int omb_gem_exclude_point(const double* d_xyz, int64_t n_c, int64_t n, double px, double py, double pz,
+                          double d_min, unsigned char* d_alive, void* stream);
+
+/* ---- weighted OLS predict, batched (replaces the per-vector pinv(W Theta) loop of SPR.predict for
+ *      measurements with non-zero uncertainties, sparse_sensing.py:871-878): for vector b
+ *        W = diag(1 / y0s[b]);  Ar[b] = argmin || W Theta a - W y0v[b] ||;  Asig[b] = | argmin || W Theta a - y0s[b] || |
+ *      by Householder QR of W Theta (s x r, s >= r) in shared memory, one CTA per vector.  flag[b] = 1 (and no
+ *      output) when min|R_kk| <= rank_tol * max|R_kk|: not full column rank, take the pseudo-inverse route.
+ *      omb_wols_smem_bytes(s, r) must not exceed 227 KB. */
+int64_t omb_wols_smem_bytes(int64_t s, int64_t r);
+int omb_wols_predict(const double* d_Theta, int64_t s, int64_t r, const double* d_y0v, const double* d_y0s,
+                     int64_t N, double rank_tol, double* d_Ar, double* d_Asig, int* d_flag, void* stream);
+
+/* ---- general (non-one-hot) measurement / sampling matrices in CSR form: replaces
+ *      Theta = C.dot(Ur) (sparse_sensing.py:797), C.dot(X_cnt) (:573) and the sampled scale / centre of
+ *      unscale_data / reconstruct(sampling=) (:233, :365-368) for scipy CSR matrices such as the line-of-sight
+ *      matrices of utils.camera.project (utils.py:318-469).  Never densified.  indices are LOCAL row indices
+ *      (row-sharded runs pass the columns of C that fall on the rank's rows and sum the partial results in rank
+ *      order).  d_Theta (s x r), d_cnt_s (s), d_scl_s (s): any may be NULL.  d_ws: omb_csr_ws_bytes(). */
+int64_t omb_csr_ws_bytes(int64_t s, int64_t max_row_nnz, int64_t r);
+int omb_csr_times_basis(const int64_t* d_indptr, const int64_t* d_indices, const double* d_data, int64_t s,
+                        int64_t max_row_nnz, const double* d_Ut, int64_t n, int64_t r, const double* d_cnt,
+                        const double* d_scl, int64_t n_c, double* d_Theta, double* d_cnt_s, double* d_scl_s,
+                        void* d_ws, void* stream);
 
 /* ---- K8/K9: train = row gather (replaces the dense C.dot(Ur), C.dot(X_cnt);
  *      sparse_sensing.py:797, :573).  d_Theta is s x r row-major, d_cnt_s may be NULL. -------- */

@@ -52,6 +52,11 @@ SIGNATURES = {
     "omb_gem_variance": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "omb_gem_step": (_int, [_vp, _i64, _i64, C.c_double, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "omb_gem_exclude": (_int, [_vp, _i64, _i64, _vp, C.c_double, _vp, _vp]),
+    "omb_gem_exclude_point": (_int, [_vp, _i64, _i64, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp]),
+    "omb_wols_smem_bytes": (_i64, [_i64, _i64]),
+    "omb_wols_predict": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp]),
+    "omb_csr_ws_bytes": (_i64, [_i64, _i64, _i64]),
+    "omb_csr_times_basis": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "omb_gather_rows": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "omb_modes_to_rows": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "omb_rows_to_modes": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -153,6 +153,19 @@ gem_exclude_kernel(const double* __restrict__ xyz, int64_t n_c, int64_t n, const
     }
 }
 
+// the same exclusion around a point given by its coordinates (multi-rank: the chosen cell may live on a peer)
+__global__ void __launch_bounds__(256)
+gem_exclude_point_kernel(const double* __restrict__ xyz, int64_t n_c, int64_t n, double px, double py, double pz,
+                         double d_min, unsigned char* __restrict__ alive)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = j % n_c;
+        const double dx = px - xyz[c * 3 + 0], dy = py - xyz[c * 3 + 1], dz = pz - xyz[c * 3 + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        if (!(d >= d_min)) alive[j] = 0;
+    }
+}
+
 template <int KB>
 static int launch_gem_step(const double* Ut, int64_t n, int r, double coef, int k, const double* Z, const double* B,
                            const double* var, const unsigned char* alive, GemCand* cand, int grid, cudaStream_t st)
@@ -215,4 +228,15 @@ extern "C" int omb_gem_exclude(const double* d_xyz, int64_t n_c, int64_t n, cons
     if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
     gem_exclude_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_xyz, n_c, n, d_sensor, d_min, d_alive);
     return check_launch("gem_exclude_kernel");
+}
+
+extern "C" int omb_gem_exclude_point(const double* d_xyz, int64_t n_c, int64_t n, double px, double py, double pz,
+                                     double d_min, unsigned char* d_alive, void* stream)
+{
+    OMB_CHECK_ARG(d_xyz && d_alive, "null pointer");
+    OMB_CHECK_ARG(n_c > 0 && n > 0, "non-positive size");
+    int64_t g = ceil_div(n, 256);
+    if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
+    gem_exclude_point_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_xyz, n_c, n, px, py, pz, d_min, d_alive);
+    return check_launch("gem_exclude_point_kernel");
 }

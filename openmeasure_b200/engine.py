@@ -461,8 +461,6 @@ class Engine:
         the basis per sensor; the k x k covariance inverse (with the reference's random jitter, drawn
         through `normal` exactly where the reference calls np.random.normal) is formed on the host
         from the chosen rows.  Returns the sensor row indices (numpy int64)."""
-        if self.world > 1:
-            raise NotImplementedError("GEM placement is single-rank in this build")
         L = _lib.load()
         if n_sensors > int(L.omb_gem_max_sensors()):
             raise ValueError("n_sensors exceeds the supported %d" % int(L.omb_gem_max_sensors()))
@@ -471,16 +469,21 @@ class Engine:
         Ut = self.Ut if Ut is None else Ut
         r = int(Ut.shape[1])
         n, st = self.n_loc, _stream()
+        multi = self.world > 1
         var = torch.empty(n, dtype=torch.float64, device=self.dev)
         _lib.call("omb_gem_variance", _p(Ut), n, r, _p(var), st)
         alive = torch.ones(n, dtype=torch.uint8, device=self.dev) if mask_dev is None \
             else mask_dev.to(torch.uint8).contiguous()
-        sigma_max = float(torch.where(alive.bool(), var, torch.full_like(var, -1.0)).max())
+        smax = torch.where(alive.bool(), var, torch.full_like(var, -1.0)).max().reshape(1)
+        if multi:                                          # the largest variance over ALL ranks' live candidates
+            smax = self.comm.allgather(smax).max().reshape(1)
+        sigma_max = float(smax)
         coef = 1 / np.sqrt(sigma_max) * 2                  # :622
         ws = _ws(L.omb_gem_ws_bytes(), self.dev)
         idx = torch.empty(1, dtype=torch.int64, device=self.dev)
         val = torch.empty(1, dtype=torch.float64, device=self.dev)
         row = torch.empty(r, dtype=torch.float64, device=self.dev)
+        rec = torch.empty(5 + r, dtype=torch.float64, device=self.dev) if multi else None
         sensors, rows, H_tot = [], [], 0.0
         if verbose:
             print(f"{'-'*70} \n {'# sensors':^10} {'sigma^2 y':^10} {'sigma^2 y|a':^10} {'Htot':^10} \n ")
@@ -493,25 +496,49 @@ class Engine:
                     B = np.atleast_2d(1 / Sigma_aa)        # :663
                 else:
                     noise = 1e-5 * normal(Sigma_aa.shape[0])           # :667
+                    if multi:                              # one jitter for all ranks: rank 0's draw
+                        noise = self.comm.allgather(torch.from_numpy(noise).to(self.dev))[0].cpu().numpy()
                     B = np.linalg.inv(Sigma_aa + np.diag(noise))
                 Zd = torch.from_numpy(np.ascontiguousarray(A - A.mean(axis=1, keepdims=True))).to(self.dev)
                 Bd = torch.from_numpy(np.ascontiguousarray(B)).to(self.dev)
             _lib.call("omb_gem_step", _p(Ut), n, r, C.c_double(coef), k, _p(Zd), _p(Bd), _p(var), _p(alive), _p(ws),
                       _p(idx), _p(val), _p(row), st)
-            if d_min > 0.0:                                # :646-649 (d_min == 0 keeps every candidate)
-                _lib.call("omb_gem_exclude", _p(xyz_dev), self.n_c_loc, n, _p(idx), C.c_double(d_min), _p(alive), st)
-            i = int(idx.item())
-            if i < 0:
-                break                                      # every candidate excluded
+            if not multi:
+                if d_min > 0.0:                            # :646-649 (d_min == 0 keeps every candidate)
+                    _lib.call("omb_gem_exclude", _p(xyz_dev), self.n_c_loc, n, _p(idx), C.c_double(d_min), _p(alive), st)
+                i = int(idx.item())
+                if i < 0:
+                    break                                  # every candidate excluded
+                v, var_i, row_h = float(val.item()) if verbose else 0.0, None, row.cpu().numpy().copy()
+            else:
+                # row-sharded: every rank offers its local winner (value, GLOBAL index, coordinates, basis row); the
+                # largest value wins, ties go to the lowest global index like np.argmax over the whole basis (:681)
+                il = int(idx.item())
+                rec.zero_()
+                rec[0] = val[0] if il >= 0 else float("-inf")
+                rec[1] = float(self.layout.to_global(torch.tensor([max(il, 0)])).item()) if il >= 0 else -1.0
+                if il >= 0:
+                    if xyz_dev is not None:
+                        rec[2:5] = xyz_dev[il % self.n_c_loc]
+                    rec[5:] = row
+                allr = self.comm.allgather(rec).cpu().numpy()
+                live = allr[:, 1] >= 0
+                if not live.any():
+                    break
+                best = max((g for g in range(self.world) if live[g]), key=lambda g: (allr[g, 0], -allr[g, 1]))
+                i, v, row_h = int(allr[best, 1]), float(allr[best, 0]), allr[best, 5:].copy()
+                if d_min > 0.0:
+                    _lib.call("omb_gem_exclude_point", _p(xyz_dev), self.n_c_loc, n, C.c_double(allr[best, 2]),
+                              C.c_double(allr[best, 3]), C.c_double(allr[best, 4]), C.c_double(d_min), _p(alive), st)
             sensors.append(i)
-            rows.append(row.cpu().numpy().copy())
+            rows.append(row_h)
             if verbose:
-                v = float(val.item())
                 if s == 0:
                     print(f"{s+1:^10} {v:^10.2e} {'  -':^10} {'  -':^10}")
                 else:
                     H_tot += 0.5 * np.log(v) + 0.5 * (np.log(2 * np.pi) + 1)
-                    print(f"{s+1:^10} {float(var[i]) * coef**2:^10.2e} {v:^10.2e} {H_tot:^10.2e}")
+                    var_s = float(np.var(row_h * coef, ddof=1))
+                    print(f"{s+1:^10} {var_s:^10.2e} {v:^10.2e} {H_tot:^10.2e}")
         return np.asarray(sensors, dtype=np.int64)
 
     # ------------------------------------------------------------------------------- K8 - K11
@@ -533,6 +560,45 @@ class Engine:
         both = self.comm.sum_ordered(both.contiguous())                  # one non-zero term per row
         return both[:, : self.r].contiguous(), both[:, self.r].contiguous()
 
+    def local_columns(self, M):
+        """The columns of a (s x n_global) scipy-sparse / dense matrix that fall on this rank's rows, as a scipy CSR
+        matrix with LOCAL column indices (single rank: the matrix itself in CSR form)."""
+        import scipy.sparse as sp
+        M = M.tocsr() if sp.issparse(M) else sp.csr_matrix(np.asarray(M, dtype=np.float64))
+        if self.world > 1:
+            cols = self.layout.to_global(torch.arange(self.n_loc)).numpy()
+            M = M.tocsc()[:, cols].tocsr()
+        M.sort_indices()
+        return M
+
+    def csr_apply(self, M, want_basis=True):
+        """(M U_r, M cnt, M scl_rows) for a general matrix M (s x n_global; sparse never densified): the CSR kernel on
+        this rank's columns, partial results summed over the ranks in rank order.  M U_r is None without a basis."""
+        M = self.local_columns(M)
+        s = int(M.shape[0])
+        r = int(self.r) if (want_basis and self.Ut is not None) else 0
+        indptr = torch.from_numpy(M.indptr.astype(np.int64)).to(self.dev)
+        indices = torch.from_numpy(M.indices.astype(np.int64)).to(self.dev)
+        data = torch.from_numpy(M.data.astype(np.float64)).to(self.dev)
+        max_nnz = int(np.diff(M.indptr).max()) if s else 0
+        if self.world > 1:                               # the same launch geometry is not required, only the sums
+            pass
+        out = torch.zeros(s, r + 2, dtype=torch.float64, device=self.dev)
+        Theta = torch.empty(s, max(r, 1), dtype=torch.float64, device=self.dev)
+        cs = torch.empty(s, dtype=torch.float64, device=self.dev)
+        ss = torch.empty(s, dtype=torch.float64, device=self.dev)
+        ws = _ws(_lib.load().omb_csr_ws_bytes(s, max_nnz, r), self.dev)
+        _lib.call("omb_csr_times_basis", _p(indptr), _p(indices if indices.numel() else None), _p(data if data.numel() else None),
+                  s, max_nnz, _p(self.Ut if r else None), self.n_loc, r, _p(self.cnt), _p(self.scl), self.n_c_loc,
+                  _p(Theta if r else None), _p(cs), _p(ss), _p(ws), _stream())
+        if r:
+            out[:, :r] = Theta
+        out[:, r] = cs
+        out[:, r + 1] = ss
+        if self.world > 1:
+            out = self.comm.sum_ordered(out.contiguous())
+        return (out[:, :r].contiguous() if r else None), out[:, r].contiguous(), out[:, r + 1].contiguous()
+
     def ols_predict(self, Y_dev, cnt_s, scl_s, PinvT):
         N, s = (int(v) for v in Y_dev.shape)
         r = int(PinvT.shape[1])
@@ -540,6 +606,29 @@ class Engine:
         _lib.call("omb_ols_predict", _p(Y_dev.contiguous()), _p(cnt_s), _p(scl_s), _p(PinvT.contiguous()),
                   N, s, r, _p(A), _stream())
         return A
+
+    def wols_predict(self, Theta, y0v, y0s):
+        """Weighted OLS for Nw vectors (y0v, y0s: (Nw, s) scaled values / uncertainties): (Ar, Ar_sigma), each
+        (Nw, r).  One CTA per vector (Householder QR of diag(1/y0s) Theta in shared memory); vectors whose weighted
+        Theta is not of full column rank -- and shapes beyond the shared-memory factorisation -- take the batched
+        pseudo-inverse the reference's np.linalg.pinv defines."""
+        Theta = Theta.contiguous()
+        s, r = (int(v) for v in Theta.shape)
+        Nw = int(y0v.shape[0])
+        Ar = torch.zeros(Nw, r, dtype=torch.float64, device=self.dev)
+        As = torch.zeros(Nw, r, dtype=torch.float64, device=self.dev)
+        todo = torch.arange(Nw, device=self.dev)
+        if s >= r and int(_lib.load().omb_wols_smem_bytes(s, r)) <= 227 * 1024:
+            flag = torch.zeros(Nw, dtype=torch.int32, device=self.dev)
+            _lib.call("omb_wols_predict", _p(Theta), s, r, _p(y0v), _p(y0s), Nw, C.c_double(1e-13), _p(Ar), _p(As), _p(flag),
+                      _stream())
+            todo = torch.nonzero(flag).flatten()
+        if todo.numel():
+            Wt = (1.0 / y0s[todo]).unsqueeze(2) * Theta.unsqueeze(0)           # diag(1/sigma) Theta
+            P = torch.linalg.pinv(Wt, rtol=1e-15)
+            Ar[todo] = torch.bmm(P, (y0v[todo] / y0s[todo]).unsqueeze(2)).squeeze(2)
+            As[todo] = torch.bmm(P, y0s[todo].unsqueeze(2)).squeeze(2).abs()
+        return Ar, As
 
     def reconstruct(self, A_dev, row0=0, nrows=None, out=None):
         """rows [row0, row0+nrows) of scl * (U_r A^T) + cnt, as a (nrows, N) device tensor."""

@@ -75,6 +75,19 @@ class SensorMatrix:
     __matmul__ = dot
 
 
+def _check_rows(piv, n):
+    """Row indices of a one-hot matrix must address rows of X (the reference's dense C cannot hold anything else)."""
+    piv = np.asarray(piv)
+    if piv.size and (piv.min() < 0 or piv.max() >= n):
+        raise IndexError('sensor index out of range: C has a 1 outside the %d rows of X' % n)
+
+
+def _one_hot_csr(piv, n):
+    import scipy.sparse as sp
+    piv = np.asarray(piv, dtype=np.int64)
+    return sp.csr_matrix((np.ones(piv.size), (np.arange(piv.size), piv)), shape=(piv.size, n))
+
+
 def _as_pivots(C):
     """pivots of a one-hot C (SensorMatrix or dense), else None."""
     if isinstance(C, SensorMatrix):
@@ -284,23 +297,17 @@ class ROM:
             raise ValueError('The number of columns of the sampling matrix does not match the number'
                              ' of rows of X.')
         piv = _as_pivots(sampling)
-        if piv is not None and eng.world == 1:
-            pd = torch.from_numpy(piv).to(eng.dev)
-            SU, cnt_s = (eng.gather(pd) if eng.Ut is not None else (None, eng.cnt[pd]))
-            scl_s = eng.scl[pd // eng.n_c_loc]
-            return SU, scl_s, cnt_s
-        if eng.world > 1:
-            raise NotImplementedError('general sampling matrices are single-rank in this build')
-        Sd = self._dense_to_device(sampling, eng)
-        SU = Sd @ eng.basis_rows() if eng.Ut is not None else None
-        scl_rows = torch.repeat_interleave(eng.scl, eng.n_c_loc)
-        return SU, Sd @ scl_rows, Sd @ eng.cnt
-
-    @staticmethod
-    def _dense_to_device(C, eng):
-        if hasattr(C, "toarray") and not isinstance(C, np.ndarray):
-            C = C.toarray()
-        return torch.from_numpy(np.ascontiguousarray(C, dtype=np.float64)).to(eng.dev)
+        if piv is not None:
+            _check_rows(piv, self._n_rows())
+            if eng.world == 1:
+                pd = torch.from_numpy(piv).to(eng.dev)
+                SU, cnt_s = (eng.gather(pd) if eng.Ut is not None else (None, eng.cnt[pd]))
+                scl_s = eng.scl[pd // eng.n_c_loc]
+                return SU, scl_s, cnt_s
+            sampling = _one_hot_csr(piv, self._n_rows())      # row-sharded: the same CSR path, one term per row
+        # general matrix (dense, or scipy sparse such as utils.camera.project's line-of-sight CSR): never densified
+        SU, cnt_s, scl_s = eng.csr_apply(sampling)
+        return SU, scl_s, cnt_s
 
     def unscale_data(self, x0, sampling=None):
         """x = X_scl * x0 + X_cnt, or (S X_scl) * x0 + S X_cnt (sparse_sensing.py:212-240)."""
@@ -677,12 +684,12 @@ class SPR(ROM):
             self.C = C
             piv = _as_pivots(C)
             if piv is not None:
+                _check_rows(piv, n)
                 Theta_d, cnt_s = eng.gather(torch.from_numpy(piv).to(eng.dev))
-            else:
-                Cd = self._dense_to_device(C, eng)
-                Ur_d = eng.basis_rows()
-                Theta_d = Cd @ Ur_d
-                cnt_s = Cd @ eng.cnt
+            else:                                          # general C: CSR kernel, row-sharded like everything else
+                if eng.Ut is None:
+                    raise AttributeError('The function fit has to be called before calling train.')
+                Theta_d, cnt_s, _ = eng.csr_apply(C)
             self._cnt_s = cnt_s
         else:
             Theta_d = torch.from_numpy(np.ascontiguousarray(C, dtype=np.float64)).to(eng.dev)
@@ -738,6 +745,9 @@ class SPR(ROM):
         eng = self._engine()
         N = len(y)
         Y = np.stack([np.asarray(yi, dtype=np.float64) for yi in y])        # (N, s, 3)
+        fid = Y[:, :, 2]
+        if fid.size and (fid.min() < 0 or fid.max() >= self.n_features):     # the reference's X_scl[id * n_points] (:576)
+            raise IndexError('feature index out of range in y[:, 2]')
         Yd = torch.from_numpy(Y).to(eng.dev)
         scl_s = eng.scl[Yd[:, :, 2].to(torch.int64)]                         # (N, s)
         cnt_s = self._cnt_s
@@ -756,11 +766,10 @@ class SPR(ROM):
                 Ar[idx] = eng.ols_predict(Y0.contiguous(), None, None, self._PinvT)
         if bool(weighted.any()):                                             # :871-878
             idx = torch.nonzero(weighted).flatten()
-            y0v = (Yd[idx, :, 0] - cnt_s) / scl_s[idx]
-            y0s = Yd[idx, :, 1] / scl_s[idx]
-            Wt = (1.0 / y0s).unsqueeze(2) * self._Theta_d.unsqueeze(0)       # diag(1/sigma) Theta
-            P = torch.linalg.pinv(Wt, rtol=1e-15)                            # (Nw, r, s)
-            Ar[idx] = torch.bmm(P, (y0v / y0s).unsqueeze(2)).squeeze(2)
-            Asig[idx] = torch.bmm(P, y0s.unsqueeze(2)).squeeze(2).abs()
+            y0v = ((Yd[idx, :, 0] - cnt_s) / scl_s[idx]).contiguous()
+            y0s = (Yd[idx, :, 1] / scl_s[idx]).contiguous()
+            a_w, s_w = eng.wols_predict(self._Theta_d, y0v, y0s)
+            Ar[idx] = a_w
+            Asig[idx] = s_w
         self.scale_vector(y[-1])                # leaves cnt_vector / scl_vector like the reference
         return Ar.cpu().numpy(), Asig.cpu().numpy()

@@ -829,6 +829,156 @@ def test_api_extras_match_reference_golden(torch_cuda):
     np.testing.assert_allclose(spr.unscale_data(z["x0"], sampling=z["S"]), z["x_uns"], rtol=1e-13)
 
 
+@pytest.mark.parametrize("n_sensors,d_min", [(10, 0.0), (16, 0.06)])
+def test_gem_row_sharded_matches_single_rank(torch_cuda, n_sensors, d_min):
+    """GEM over a row-sharded basis (thread-emulated ranks): every rank offers its local winner, the largest value
+    (lowest global index on ties) wins -- the selection must be the single-rank one, on every rank."""
+    import threading
+    torch = torch_cuda
+    from oracle import synth as osynth
+    from openmeasure_b200 import comm as C, engine as E
+    F, m, r = 3, 40, 20
+    cells = [900, 700, 1100]
+    n_c = sum(cells)
+    X = osynth.snapshots(F, n_c, m, r)
+    rng = np.random.default_rng(11)
+    xyz = rng.random((n_c, 3))
+    mask = rng.random(F * n_c) > 0.15
+    one = _sps().SPR(X, F, xyz)
+    one.fit(select_modes="number", n_modes=r)
+    Ur = one.Ur
+    draws = [rng.standard_normal(k) for k in range(n_sensors + 1)]
+    take = lambda seq: (lambda size: seq.pop(0)[:size])
+    ref = one._eng.gem(n_sensors, torch.from_numpy(mask).cuda(), torch.from_numpy(xyz).cuda(), d_min,
+                       normal=take([d.copy() for d in draws[2:]]))
+    comms = C.ThreadComm.make(len(cells))
+    out, err = [None] * len(cells), []
+
+    def run(rk):
+        try:
+            lay = C.ShardLayout(F, cells, rk)
+            rows = lay.to_global(torch.arange(F * cells[rk])).numpy()
+            eng = E.Engine(torch.from_numpy(np.ascontiguousarray(X[rows])).cuda(), F, comm=comms[rk])
+            eng.set_basis_rows(torch.from_numpy(np.ascontiguousarray(Ur[rows])).cuda())
+            xl = xyz[lay.cell0:lay.cell0 + cells[rk]]
+            out[rk] = eng.gem(n_sensors, torch.from_numpy(mask[rows]).cuda(), torch.from_numpy(np.ascontiguousarray(xl)).cuda(),
+                              d_min, normal=take([d.copy() for d in draws[2:]]))
+        except Exception as e:          # pragma: no cover
+            err.append(e)
+            comms[rk].shared.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(k,)) for k in range(len(cells))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if err:
+        raise err[0]
+    for o in out:
+        np.testing.assert_array_equal(o, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY 8f rows 2 and 3 on repo kernels: weighted OLS (batched Householder QR) and general CSR measurement matrices
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s,r,N", [(12, 12, 5), (40, 24, 33), (100, 100, 64), (150, 90, 10)])
+def test_weighted_ols_kernel_matches_pinv_loop(torch_cuda, s, r, N):
+    """SPR.predict's weighted branch (sparse_sensing.py:871-878) per vector with np.linalg.pinv, against the batched
+    QR kernel; one vector gets a rank-deficient weighted Theta and must come back through the pseudo-inverse route."""
+    torch = torch_cuda
+    from openmeasure_b200 import engine as E
+    rng = np.random.default_rng(s * r + N)
+    Theta = rng.standard_normal((s, r))
+    y0v = rng.standard_normal((N, s))
+    y0s = 0.05 + rng.random((N, s))
+    eng = E.Engine(torch.zeros(8, 4, dtype=torch.float64, device="cuda"), 1, group=False)
+    a, sg = eng.wols_predict(torch.from_numpy(Theta).cuda(), torch.from_numpy(y0v).cuda(), torch.from_numpy(y0s).cuda())
+    a, sg = a.cpu().numpy(), sg.cpu().numpy()
+    for b in range(N):
+        W = np.diag(1 / y0s[b])
+        P = np.linalg.pinv(W @ Theta)
+        np.testing.assert_allclose(a[b], P @ (W @ y0v[b]), rtol=1e-9, atol=1e-9 * np.abs(a[b]).max())
+        np.testing.assert_allclose(sg[b], np.abs(P @ y0s[b]), rtol=1e-9, atol=1e-9 * np.abs(sg[b]).max())
+    Th2 = Theta.copy()
+    Th2[:, -1] = Th2[:, 0]                                             # rank deficient: the kernel must flag it
+    a2, _ = eng.wols_predict(torch.from_numpy(Th2).cuda(), torch.from_numpy(y0v[:2]).cuda(), torch.from_numpy(y0s[:2]).cuda())
+    for b in range(2):
+        W = np.diag(1 / y0s[b])
+        np.testing.assert_allclose(a2[b].cpu().numpy(), np.linalg.pinv(W @ Th2, rcond=1e-15) @ (W @ y0v[b]), rtol=1e-6, atol=1e-8)
+
+
+def test_general_csr_matrix_never_densified_and_row_sharded(torch_cuda, monkeypatch):
+    """train(C) / reconstruct(sampling=) with a scipy CSR line-of-sight style matrix: equals the dense products of the
+    reference (sparse_sensing.py:797, :573, :365-368), never calls toarray(), and gives the same Theta when the rows
+    are sharded over (thread-emulated) ranks."""
+    import threading
+    import scipy.sparse as sp
+    torch = torch_cuda
+    from oracle import pod_oracle as po, synth as osynth
+    from openmeasure_b200 import comm as Cm
+    F, m, r, s = 3, 32, 10, 17
+    cells = [500, 420, 380]
+    n_c = sum(cells)
+    n = F * n_c
+    X = osynth.snapshots(F, n_c, m, r)
+    rng = np.random.default_rng(5)
+    Cs = sp.random(s, n, density=0.01, format="csr", random_state=3, data_rvs=lambda k: rng.random(k) + 0.1)
+    Cs[0, :] = 0                                                       # an empty row
+    Cs.eliminate_zeros()
+    dense = Cs.toarray()
+    monkeypatch.setattr(sp.csr_matrix, "toarray", lambda *a, **k: (_ for _ in ()).throw(AssertionError("densified")))
+    monkeypatch.setattr(sp.csr_matrix, "todense", lambda *a, **k: (_ for _ in ()).throw(AssertionError("densified")))
+    one = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    one.fit(select_modes='number', n_modes=r)
+    one.train(Cs, cond=True)
+    Ur = one.Ur
+    np.testing.assert_allclose(one.Theta, dense @ Ur, rtol=0, atol=1e-12 * np.abs(dense @ Ur).max())
+    np.testing.assert_allclose(one._cnt_s.cpu().numpy(), dense @ one.X_cnt[:, 0], rtol=1e-12)
+    A = rng.standard_normal((4, r))
+    np.testing.assert_allclose(one.reconstruct(A, sampling=Cs),
+                               (dense @ one.X_scl[:, 0])[:, None] * ((dense @ Ur) @ A.T) + (dense @ one.X_cnt[:, 0])[:, None],
+                               rtol=1e-10, atol=1e-10)
+    comms = Cm.ThreadComm.make(len(cells))
+    out, err = [None] * len(cells), []
+
+    def run(rk):
+        try:
+            lay = Cm.ShardLayout(F, cells, rk)
+            rows = lay.to_global(torch.arange(F * cells[rk])).numpy()
+            spr = _sps().SPR.from_device(torch.from_numpy(np.ascontiguousarray(X[rows])).cuda(), F, comm=comms[rk])
+            spr.fit(select_modes='number', n_modes=r)
+            spr.train(Cs)
+            out[rk] = (spr.Theta.copy(), spr._cnt_s.cpu().numpy().copy())
+        except Exception as e:          # pragma: no cover
+            err.append(e)
+            comms[rk].shared.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(k,)) for k in range(len(cells))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if err:
+        raise err[0]
+    for Th, cs in out:
+        np.testing.assert_allclose(np.abs(Th), np.abs(one.Theta), rtol=0, atol=1e-10 * np.abs(one.Theta).max())
+        np.testing.assert_allclose(cs, one._cnt_s.cpu().numpy(), rtol=1e-12)
+    np.testing.assert_array_equal(out[0][0], out[1][0])                # identical bits on every rank
+
+
+def test_bad_sensor_and_feature_indices_raise_index_error(torch_cuda):
+    from oracle import synth as osynth
+    F, n_c, m, r = 2, 300, 16, 6
+    X = osynth.snapshots(F, n_c, m, r)
+    spr = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    spr.fit(select_modes='number', n_modes=r)
+    C = spr.optimal_placement()
+    bad = _sps().SensorMatrix(np.array([0, 5, F * n_c + 3, 7, 8, 9]), F * n_c)
+    with pytest.raises(IndexError):
+        spr.train(bad)
+    spr.train(C)
+    y = np.zeros((r, 3))
+    y[:, 2] = F                                                        # feature id out of range
+    with pytest.raises(IndexError):
+        spr.predict(y)
+
+
 # ---------------------------------------------------------------------------------------------
 # streamed reconstruct (configs[3]: the n x N result never exists on the device): row chunks through the
 # two-buffer ring must equal the one-shot result bit for bit, for every `out` form
