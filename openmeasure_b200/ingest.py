@@ -104,6 +104,10 @@ def load_npy_shard(path, n_features, rank=0, world=1, device=None, chunk_bytes=C
     th = threading.Thread(target=reader, daemon=True)
     th.start()
     copy_stream = torch.cuda.Stream(device=device)
+    # `out` was allocated on the current stream: a block the caching allocator recycled may still have kernels of its
+    # previous owner pending there, so the copies wait for that stream, and the block is tied to the copy stream
+    copy_stream.wait_stream(torch.cuda.current_stream(device))
+    out.record_stream(copy_stream)
     events = [None] * nbuf
     with torch.cuda.stream(copy_stream):
         for i, (_, nb, dst) in enumerate(plan):
