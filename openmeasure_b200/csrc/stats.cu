@@ -229,12 +229,28 @@ __device__ __forceinline__ double upsweep_level(double v, int sl, int half, int 
     return v;
 }
 
+// (offset, length) of every depth-LW node of numpy's tree over block_elems elements (length -1: the node does not
+// exist, its range ended in a leaf higher up).  The walk from the root is ~20 levels of dependent 64-bit integer
+// work; done per node inside the sweep it sat between two batches of loads and kept a third of the warps' time
+// without memory requests in flight (3.8 - 4.5 TB/s).  One table per call, shared by all features.
+__global__ void __launch_bounds__(256)
+node_table_kernel(int64_t block_elems, int LW, int64_t* __restrict__ table)
+{
+    const int64_t nwn = (int64_t)1 << LW;
+    for (int64_t wn = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wn < nwn; wn += (int64_t)gridDim.x * blockDim.x) {
+        int64_t off = 0, n = block_elems;
+        const bool present = descend(off, n, (uint32_t)wn, LW);
+        table[2 * wn] = off;
+        table[2 * wn + 1] = present ? n : -1;
+    }
+}
+
 template <int MODE>   // 0: sum/min/max   1: sum of squared deviations about stats[f*4]/count
 __global__ void __launch_bounds__(BS_THREADS, BS_CTAS_PER_SM)
 block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LW, int LQ,
                   const double* __restrict__ stats, double mean_count, double* __restrict__ top_val,
                   unsigned char* __restrict__ top_flag, double* __restrict__ cta_min,
-                  double* __restrict__ cta_max)
+                  double* __restrict__ cta_max, const int64_t* __restrict__ table)
 {
     const int f = blockIdx.y;
     const int64_t nwn = (int64_t)1 << LW;
@@ -249,9 +265,13 @@ block_tree_kernel(const double* __restrict__ X, int64_t block_elems, int LW, int
     double lo = __longlong_as_double(0x7FF0000000000000LL), hi = -lo;
 
     const int64_t nwarps = (int64_t)gridDim.x * (BS_THREADS / 32);
-    for (int64_t wn = (int64_t)blockIdx.x * (BS_THREADS / 32) + warp; wn < nwn; wn += nwarps) {
-        int64_t off = 0, n = block_elems;
-        const bool present = descend(off, n, (uint32_t)wn, LW);
+    int64_t wn = (int64_t)blockIdx.x * (BS_THREADS / 32) + warp;
+    longlong2 nxt = make_longlong2(0, -1);
+    if (wn < nwn) nxt = *reinterpret_cast<const longlong2*>(table + 2 * wn);
+    for (; wn < nwn; wn += nwarps) {
+        int64_t off = nxt.x, n = nxt.y;
+        const bool present = n >= 0;
+        if (wn + nwarps < nwn) nxt = *reinterpret_cast<const longlong2*>(table + 2 * (wn + nwarps));   // next node's range
         double v = 0.0;
         bool here = false;
         if (present && sl < nslots) {
@@ -553,8 +573,9 @@ extern "C" int64_t omb_block_stats_ws_bytes(int64_t F, int64_t block_elems)
     if (F <= 0 || block_elems <= 0) return 0;
     BlockPlan p = make_plan(block_elems);
     int64_t ntop = (int64_t)1 << p.LW;
-    // level-LW values + flags, per-CTA min/max partials, per feature
-    return F * ntop * (int64_t)sizeof(double) + round_up(F * ntop, 256) + 2 * F * BS_GX_MAX * (int64_t)sizeof(double) + 256;
+    // level-LW values + flags, per-CTA min/max partials, per feature; the node table (offset, length per node)
+    return F * ntop * (int64_t)sizeof(double) + round_up(F * ntop, 256) + 2 * F * BS_GX_MAX * (int64_t)sizeof(double) + 256 +
+           2 * ntop * (int64_t)sizeof(int64_t);
 }
 
 extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems, int mode,
@@ -570,6 +591,14 @@ extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems
     double* top_min = top_val + F * ntop;
     double* top_max = top_min + F * BS_GX_MAX;
     unsigned char* top_flag = (unsigned char*)(top_max + F * BS_GX_MAX);
+    int64_t* table = (int64_t*)((((uintptr_t)(top_flag + round_up(F * ntop, 256))) + 15) & ~(uintptr_t)15);
+    {
+        int64_t gt = ceil_div(ntop, 256);
+        if (gt > 2048) gt = 2048;
+        node_table_kernel<<<(unsigned)gt, 256, 0, (cudaStream_t)stream>>>(block_elems, p.LW, table);
+        int rc0 = check_launch("node_table_kernel");
+        if (rc0) return rc0;
+    }
     // persistent warps: ~BS_CTAS_PER_SM CTAs per SM over all features, each warp strides over nodes
     int64_t gx = ceil_div((int64_t)sm_count() * BS_CTAS_PER_SM, F);
     const int64_t need = ceil_div(ntop, BS_THREADS / 32);
@@ -580,10 +609,10 @@ extern "C" int omb_block_stats(const double* d_X, int64_t F, int64_t block_elems
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0)
         block_tree_kernel<0><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LW, p.LQ, d_out, (double)mean_count, top_val,
-                                                           top_flag, top_min, top_max);
+                                                           top_flag, top_min, top_max, table);
     else
         block_tree_kernel<1><<<grid, BS_THREADS, 0, st>>>(d_X, block_elems, p.LW, p.LQ, d_out, (double)mean_count, top_val,
-                                                           top_flag, top_min, top_max);
+                                                           top_flag, top_min, top_max, table);
     int rc = check_launch("block_tree_kernel");
     if (rc) return rc;
     if (mode == 0)
