@@ -131,3 +131,10 @@ def test_npy_shard_ranges(tmp_path):
     np.save(p, np.asfortranarray(X))
     with pytest.raises(ValueError):
         ingest.npy_header(str(p))
+
+
+def test_reference_import_line_resolves_to_the_b200_classes():
+    """`from openmeasure.sparse_sensing import ROM, SPR` (the reference's README import) works unchanged."""
+    from openmeasure.sparse_sensing import ROM, SPR
+    from openmeasure_b200 import sparse_sensing as b
+    assert ROM is b.ROM and SPR is b.SPR and issubclass(SPR, ROM)
