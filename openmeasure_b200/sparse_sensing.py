@@ -138,6 +138,17 @@ class ROM:
     # runs.  'auto' | True (always correct) | 'full' (always full width) | False.
     pod_refine = 'auto'
     pod_refine_tol = 1e-11
+    # Extension: devices one process drives behind this very constructor.  None (or one id): the current CUDA
+    # device.  'all' or a list of ids (or OMB_DEVICES=all | 0,1,.. in the environment): the rows are sharded over
+    # those GPUs, one host thread each (openmeasure_b200/multi.py); every method keeps its reference signature.
+    devices = None
+
+    def __new__(cls, *args, **kwargs):
+        if cls is ROM or cls is SPR:
+            from . import multi as _multi
+            if len(_multi.resolve_devices(cls.devices)) > 1:
+                return object.__new__(_MultiSPR if cls is SPR else _MultiROM)
+        return object.__new__(cls)
 
     def __init__(self, X, n_features, xyz):
         if type(X) is not np.ndarray:                     # :69-70
@@ -161,7 +172,7 @@ class ROM:
         torch.distributed initialised (one process per GPU) each rank passes its own cells
         [c0, c0 + n_c_loc) of every feature; pivots / C then refer to GLOBAL row indices
         f * n_c + c, Theta / predict are replicated, reconstruct returns the local rows."""
-        self = cls.__new__(cls)
+        self = object.__new__(cls)
         if type(n_features) is not int:
             raise TypeError('The parameter n_features is not an integer.')
         if X_dev.shape[0] % n_features != 0:
@@ -773,3 +784,163 @@ class SPR(ROM):
             Asig[idx] = s_w
         self.scale_vector(y[-1])                # leaves cnt_vector / scl_vector like the reference
         return Ar.cpu().numpy(), Asig.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# one process, several GPUs, the unchanged constructor (ROM.devices / OMB_DEVICES; see multi.py)
+# ------------------------------------------------------------------------------------------------------
+_REPLICATED = ("scale_type", "Ar", "r", "Sigma_r", "Vr", "pod_sigma", "pod_rel_err_bound", "pod_refined", "qr_pivots",
+               "qr_rdiag", "qr_gap", "Theta", "k", "limits", "method", "solver", "verbose", "cnt_vector", "scl_vector")
+
+
+class _MultiROM(ROM):
+    _single = ROM
+
+    def __init__(self, X, n_features, xyz):
+        ROM.__init__(self, X, n_features, xyz)
+        from . import multi as _multi
+        _eng.require_cuda()
+        self._md = _multi.MultiDevice(self._single, X, n_features, xyz, _multi.resolve_devices(type(self).devices))
+        for s in self._md.subs:
+            s.pod_refine, s.pod_refine_tol = self.pod_refine, self.pod_refine_tol
+
+    def _engine(self):
+        raise RuntimeError('internal: the multi-device object has one engine per device')
+
+    def _pull(self):
+        s0 = self._md.subs[0]
+        for k in _REPLICATED:
+            if hasattr(s0, k):
+                setattr(self, k, getattr(s0, k))
+
+    def _rows(self, name):
+        return self._md.assemble(self._md.run(lambda s, g: getattr(s, name)))
+
+    X_cnt = property(lambda self: self._rows("X_cnt"))
+    X_scl = property(lambda self: self._rows("X_scl"))
+    X0 = property(lambda self: self._rows("X0"))
+
+    @property
+    def Ur(self):
+        return self._rows("Ur")
+
+    @Ur.setter
+    def Ur(self, v):
+        v = np.asarray(v, dtype=np.float64)
+        self._md.run(lambda s, g: setattr(s, "Ur", self._md.shard(v, g)))
+
+    def scale_data(self, scale_type='std', axis_cnt=1):
+        self._md.call("_scale_stats", scale_type, axis_cnt)
+        return self.X0
+
+    def unscale_data(self, x0, sampling=None):
+        if sampling is not None:
+            return self._md.call("unscale_data", x0, sampling)[0]
+        x0 = np.asarray(x0, dtype=np.float64)
+        return self._md.assemble(self._md.run(lambda s, g: s.unscale_data(self._md.shard(x0, g))))
+
+    def decomposition(self, X0, select_modes='variance', n_modes=99):
+        out = self._md.run(lambda s, g: s.decomposition(X0, select_modes, n_modes) if g == 0 else None)[0]
+        self.r = self._md.subs[0].r
+        return out
+
+    def fit(self, scale_type='std', axis_cnt=1, select_modes='variance', n_modes=99, basis=None):
+        if basis is None:
+            self._validate_modes(select_modes, n_modes)
+        for s in self._md.subs:
+            s.pod_refine, s.pod_refine_tol = self.pod_refine, self.pod_refine_tol
+        U = None if basis is None else np.asarray(basis[0], dtype=np.float64)
+        self._md.run(lambda s, g: s.fit(scale_type, axis_cnt, select_modes, n_modes,
+                                        None if basis is None else (self._md.shard(U, g), basis[1])))
+        self._pull()
+
+    def _pieces(self, g, row0, rows):
+        """Local rows [row0, row0 + rows) of device g as (local offset, count, global row0) runs."""
+        ncl, c0, n_c = self._md.cells[g], self._md.offsets[g], self._md.n_c
+        out, lo = [], row0
+        while lo < row0 + rows:
+            f = lo // ncl
+            hi = min(row0 + rows, (f + 1) * ncl)
+            out.append((lo - row0, hi - lo, f * n_c + c0 + (lo - f * ncl)))
+            lo = hi
+        return out
+
+    def reconstruct(self, Ar, sampling=None, *, out=None, chunk_rows=None):
+        if sampling is not None:
+            return self._md.call("reconstruct", Ar, sampling)[0]
+        Ar = np.asarray(Ar, dtype=np.float64)
+        Ar = Ar[np.newaxis, :] if Ar.ndim < 2 else Ar
+        n, N = self._md.F * self._md.n_c, Ar.shape[0]
+        sink = out if callable(out) else None
+        if sink is None:
+            if out is None:
+                out = np.empty((n, N))
+            elif out.shape != (n, N) or out.dtype != np.float64:
+                raise ValueError('out must be a float64 array of shape (n, N)')
+        import threading
+        lock = threading.Lock()
+
+        def work(s, g):
+            for row0, block in s.reconstruct_chunks(Ar, chunk_rows=chunk_rows):
+                for off, cnt, g0 in self._pieces(g, row0, block.shape[0]):
+                    if sink is None:
+                        out[g0:g0 + cnt] = block[off:off + cnt]
+                    else:
+                        with lock:
+                            sink(g0, block[off:off + cnt])
+
+        self._md.run(work)
+        return None if sink is not None else out
+
+    def reconstruct_chunks(self, Ar, chunk_rows=None):
+        for g, s in enumerate(self._md.subs):
+            with torch.cuda.device(self._md.devices[g]):
+                for row0, block in s.reconstruct_chunks(Ar, chunk_rows=chunk_rows):
+                    for off, cnt, g0 in self._pieces(g, row0, block.shape[0]):
+                        yield g0, block[off:off + cnt]
+
+
+class _MultiSPR(_MultiROM, SPR):
+    _single = SPR
+
+    def __init__(self, X, n_features, xyz):
+        _MultiROM.__init__(self, X, n_features, xyz)
+
+    def gem(self, Ur, n_sensors, mask, d_min, verbose):
+        U = None if Ur is None else np.asarray(Ur, dtype=np.float64)
+        mk = None if mask is None else np.asarray(mask, dtype=bool)
+        return self._md.run(lambda s, g: s.gem(None if U is None else self._md.shard(U, g), n_sensors,
+                                               None if mk is None else self._md.shard(mk, g), d_min,
+                                               verbose and g == 0))[0]
+
+    def optimal_placement(self, calc_type='qr', n_sensors=10, mask=None, d_min=0., verbose=False, block=8):
+        if calc_type not in ('qr', 'gem'):
+            raise NotImplementedError('The sensor selection method has not been implemented yet')
+        mk = None if mask is None else np.asarray(mask, dtype=bool)
+        C = self._md.run(lambda s, g: s.optimal_placement(calc_type, n_sensors, None if mk is None else self._md.shard(mk, g),
+                                                          d_min, verbose and g == 0, block))[0]
+        self._pull()
+        return C
+
+    def train(self, C, is_Theta=False, limits=None, method='OLS', solver='CLARABEL', cond=False, verbose=False):
+        n = self._md.F * self._md.n_c
+        if (C.shape[1] != n) and not is_Theta:
+            raise ValueError('The number of columns of C does not match the number'
+                             ' of rows of X.')
+        self._md.call("train", C, is_Theta, limits, method, solver, cond, verbose)
+        if not is_Theta:
+            self.C = C
+        self._pull()
+
+    def scale_vector(self, y):
+        out = self._md.run(lambda s, g: s.scale_vector(y) if g == 0 else None)[0]
+        self._pull()
+        return out
+
+    def predict(self, y):
+        if not hasattr(self, 'Theta'):
+            raise AttributeError('The function fit has to be called '
+                                 'before calling predict.')
+        out = self._md.run(lambda s, g: s.predict(y) if g == 0 else None)[0]      # Theta is replicated: no exchange
+        self._pull()
+        return out

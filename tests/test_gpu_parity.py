@@ -1084,3 +1084,55 @@ def test_config2_shape_pivots_match_lapack_on_device_basis(torch_cuda):
     Ur = spr.Ur
     _, _, P = sla.qr(Ur.T, pivoting=True, mode='economic')
     np.testing.assert_array_equal(spr.qr_pivots, P[:r])
+
+
+# ---------------------------------------------------------------------------------------------
+# one process, several devices, the UNCHANGED constructor (ROM.devices / OMB_DEVICES): here three "devices" that are
+# all cuda:0 (the driver's box has one GPU); tools/multi_device_check.py runs the same on real GPUs
+# ---------------------------------------------------------------------------------------------
+def test_unchanged_constructor_drives_several_devices(torch_cuda, monkeypatch):
+    from oracle import pod_oracle as po, synth as osynth
+    sps = _sps()
+    F, n_c, m, r = 3, 2300, 32, 12
+    X = osynth.snapshots(F, n_c, m, r)
+    xyz = np.random.default_rng(0).random((n_c, 3))
+    ref = po.placement_pipeline(X, F, r)
+    one = sps.SPR(X, F, xyz)
+    one.fit(select_modes='number', n_modes=r)
+    C1 = one.optimal_placement()
+    one.train(C1)
+    monkeypatch.setattr(sps.ROM, "devices", [0, 0, 0])
+    spr = sps.SPR(X, F, xyz)                                   # the reference's constructor, nothing else
+    assert type(spr).__name__ == "_MultiSPR" and isinstance(spr, sps.SPR) and spr._md.G == 3
+    spr.fit(select_modes='number', n_modes=r)
+    C = spr.optimal_placement()
+    np.testing.assert_array_equal(spr.X_cnt, ref["X_cnt"])
+    np.testing.assert_allclose(spr.X_scl, ref["X_scl"], rtol=1e-15)
+    np.testing.assert_allclose(spr.Sigma_r, ref["Sigma_r"], rtol=RTOL)
+    np.testing.assert_array_equal(C.pivots, ref["piv"])
+    Ur, _ = _sign_align(spr.Ur, ref["Ur"])
+    np.testing.assert_allclose(Ur, ref["Ur"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(spr.X0, ref["X0"] if "X0" in ref else one.X0, rtol=1e-13, atol=1e-13)
+    spr.train(C)
+    np.testing.assert_allclose(np.abs(spr.Theta), np.abs(one.Theta), rtol=0, atol=1e-10)
+    ys = []
+    for j in (1, 9):
+        y = np.zeros((r, 3))
+        y[:, 0] = X[ref["piv"], j]
+        y[:, 2] = ref["piv"] // n_c
+        ys.append(y)
+    a, _ = spr.predict(ys)
+    a1, _ = one.predict(ys)
+    np.testing.assert_allclose(np.abs(a), np.abs(a1), rtol=1e-8, atol=1e-9 * np.abs(a1).max())
+    rec, rec1 = spr.reconstruct(a, chunk_rows=256), one.reconstruct(a1)
+    np.testing.assert_allclose(rec, rec1, rtol=1e-9)
+    blocks = sorted(((g0, b.copy()) for g0, b in spr.reconstruct_chunks(a, chunk_rows=512)), key=lambda t: t[0])
+    np.testing.assert_allclose(np.vstack([b for _, b in blocks]), rec1, rtol=1e-9)
+    x0 = np.random.default_rng(1).standard_normal(F * n_c)
+    np.testing.assert_allclose(spr.unscale_data(x0), one.unscale_data(x0), rtol=1e-14)
+    mask = np.random.default_rng(2).random(F * n_c) > 0.3
+    Cg = spr.optimal_placement(calc_type='gem', n_sensors=6, mask=mask)
+    np.random.seed(0)
+    assert Cg.shape == (6, F * n_c) and mask[Cg.pivots].all()
+    with pytest.raises(ValueError):
+        spr.fit(select_modes='bogus')
