@@ -47,6 +47,11 @@ def _ws(nbytes, device):
 
 TB = 128    # candidates per basis tile (OMB_TB in csrc/common.cuh)
 
+# the framework's dense linear algebra initialises its backend lazily and not thread-safely; the multi-device mode
+# (multi.py) and the thread-emulated ranks of the tests call it from several threads
+import threading as _threading
+LINALG_LOCK = _threading.Lock()
+
 # One spare buffer per device for the centred copy of X that the many-snapshot tensor-core passes read: it is
 # as large as X itself (33 GB at config 3, 68.7 GB per GPU at config 5), lives from the Gram pass to the
 # back-projection, and is handed from fit to fit instead of going through the caching allocator each time
@@ -311,8 +316,13 @@ class Engine:
             SV = torch.empty(m + m * m, dtype=torch.float64, device=self.dev)    # sigma | V: one D2H for the host side
             V = SV[m:].view(m, m)
             _lib.call("omb_eigh_jacobi", _p(G.contiguous()), m, _p(w), _p(V), None, _stream())
+        elif self.world > 1 and self.rank != 0:
+            # library eigensolver: rank 0 solves, everybody receives its result below
+            w = torch.empty(m, dtype=torch.float64, device=self.dev)
+            V = torch.empty(m, m, dtype=torch.float64, device=self.dev)
         else:
-            w, V = torch.linalg.eigh(G)
+            with LINALG_LOCK:
+                w, V = torch.linalg.eigh(G)
             w = torch.flip(w, dims=(0,))
             V = torch.flip(V, dims=(1,))
             idx = torch.argmax(V.abs(), dim=0)
@@ -625,7 +635,8 @@ class Engine:
             todo = torch.nonzero(flag).flatten()
         if todo.numel():
             Wt = (1.0 / y0s[todo]).unsqueeze(2) * Theta.unsqueeze(0)           # diag(1/sigma) Theta
-            P = torch.linalg.pinv(Wt, rtol=1e-15)
+            with LINALG_LOCK:
+                P = torch.linalg.pinv(Wt, rtol=1e-15)
             Ar[todo] = torch.bmm(P, (y0v[todo] / y0s[todo]).unsqueeze(2)).squeeze(2)
             As[todo] = torch.bmm(P, y0s[todo].unsqueeze(2)).squeeze(2).abs()
         return Ar, As

@@ -708,15 +708,17 @@ class SPR(ROM):
             raise ValueError('The number of columns of Theta does not match the number'
                              ' of columns of Ur.')
         self._Theta_d = Theta_d
-        self._PinvT = torch.linalg.pinv(Theta_d, rtol=1e-15).T.contiguous()
+        with _eng.LINALG_LOCK:
+            self._PinvT = torch.linalg.pinv(Theta_d, rtol=1e-15).T.contiguous()
         self.Theta = Theta_d.cpu().numpy()
         self.limits = limits
         self.method = method
         self.solver = solver
         self.verbose = verbose
         if cond == True:                                  # :813-820
-            Sth = torch.linalg.svdvals(Theta_d if Theta_d.shape[0] == Theta_d.shape[1]
-                                       else torch.linalg.pinv(Theta_d, rtol=1e-15))
+            with _eng.LINALG_LOCK:
+                Sth = torch.linalg.svdvals(Theta_d if Theta_d.shape[0] == Theta_d.shape[1]
+                                           else torch.linalg.pinv(Theta_d, rtol=1e-15))
             self.k = float(Sth[0] / Sth[-1])
 
     # ------------------------------------------------------------------ predict (a9, a10)
