@@ -5,6 +5,7 @@
 // scaling 1/scl_f^2 (known only after the statistics pass) is applied to the tiny m x m result
 // and X0 is never materialised.  DMMA.8x8x4 (mma.sync m8n8k4 f64) -- tcgen05 has no FP64 kind.
 // Deterministic: fixed row split per feature, partial tiles reduced in fixed order, no atomics.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/omb200.h"
 
@@ -164,12 +165,13 @@ constexpr int GB_CENTRE_WARPS = 3;                // ... and a producer warpgrou
 constexpr int GB_THREADS = (GB_MMA_WARPS + 1 + GB_CENTRE_WARPS) * 32;
 constexpr int GB_META = 2 * GB_K * GB_LD + GB_K;  // rows | wa | wb as ints behind the centring values
 constexpr int GB_STAGE_DOUBLES = GB_META + 2;      // panel A, panel B, centring values, meta
-constexpr int GB_W_OFF = 256, GB_W_DIAG = 136;    // relative cost of a chunk (32 vs 17 DMMAs per warp and k-step + centring)
+constexpr int GB_W_OFF = 256, GB_W_DIAG = 150;    // relative cost of a chunk: 32 vs 17 DMMAs per warp and k-step, and 19 vs 12 fragment loads (measured optimum)
 
 static size_t gram_big_smem() { return sizeof(double) * GB_STAGES * GB_STAGE_DOUBLES; }
 
 struct GbPlan {
     int T, ntiles, F, P;
+    int w_off, w_diag;    // relative cost of an off-diagonal / a diagonal chunk
     int64_t nchunks;      // 16-row chunks per feature block
     int64_t Cf;           // cost of one feature block
     int64_t U;            // total cost
@@ -182,7 +184,12 @@ __host__ __device__ static inline GbPlan gb_plan(int64_t F, int64_t n_c, int64_t
     p.ntiles = p.T * (p.T + 1) / 2;
     p.F = (int)F;
     p.nchunks = ceil_div(n_c, GB_K);
-    p.Cf = p.nchunks * ((int64_t)p.T * GB_W_DIAG + (int64_t)(p.ntiles - p.T) * GB_W_OFF);
+    p.w_off = GB_W_OFF;
+    p.w_diag = GB_W_DIAG;
+#ifndef __CUDA_ARCH__
+    if (const char* e = getenv("OMB_GB_WDIAG")) { int v = atoi(e); if (v > 0 && v < 100000) p.w_diag = v; }
+#endif
+    p.Cf = p.nchunks * ((int64_t)p.T * p.w_diag + (int64_t)(p.ntiles - p.T) * p.w_off);
     p.U = p.Cf * F;
     int64_t P = sms;
     const int64_t total_chunks = p.nchunks * p.ntiles * F;
@@ -200,14 +207,14 @@ __host__ __device__ static inline void gb_locate(const GbPlan& p, int64_t u, int
     int t = 0;
     for (int ti = 0; ti < p.T; ++ti) {                // tiles row by row: (ti, ti) then (ti, ti+1 .. T-1)
         const int noff = p.T - 1 - ti;
-        const int64_t rowcost = p.nchunks * (GB_W_DIAG + (int64_t)noff * GB_W_OFF);
+        const int64_t rowcost = p.nchunks * (p.w_diag + (int64_t)noff * p.w_off);
         if (v >= rowcost) { v -= rowcost; t += 1 + noff; continue; }
-        if (v < p.nchunks * GB_W_DIAG) { c = v / GB_W_DIAG; }
+        if (v < p.nchunks * p.w_diag) { c = v / p.w_diag; }
         else {
-            v -= p.nchunks * GB_W_DIAG;
-            const int64_t k = v / (p.nchunks * GB_W_OFF);
+            v -= p.nchunks * p.w_diag;
+            const int64_t k = v / (p.nchunks * p.w_off);
             t += 1 + (int)k;
-            c = (v - k * p.nchunks * GB_W_OFF) / GB_W_OFF;
+            c = (v - k * p.nchunks * p.w_off) / p.w_off;
         }
         g = (int)f * p.ntiles + t;
         return;
