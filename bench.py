@@ -464,6 +464,8 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
     group = None if world > 1 else False
     qr_events = []
 
+    step_marks_all = []
+
     def step():
         spr = SPR.from_device(Xd, F, group=group)
         spr.fit(scale_type=w["scale_type"], select_modes="number", n_modes=r)
@@ -472,10 +474,12 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
         C = spr.optimal_placement(block=QR_BLOCK)
         e1.record()
         qr_events.append((e0, e1))
+        step_marks_all.append(spr._eng.marks)
         return spr, C
 
     # warm-up: W steps (>= 3) and at least 0.25 s, identical to the timed steps (same object lifetimes: the caching
     # allocator reaches its steady state; the NVML sampler gets its slow first polls done under load)
+    eng_mod.Engine.trace = True
     n_warm = max(warmup, 3)
     t_w, k_w = time.perf_counter(), 0
     while True:
@@ -490,6 +494,7 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
             break
     ctx.sync_all()
     qr_events.clear()
+    step_marks_all.clear()
     L.omb_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.sync_all()
@@ -512,36 +517,24 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
     ms_per_step = ms / steps
     value = x_bytes_glob / (ms_per_step * 1e-3) / 1e9
 
-    # ---- per-stage device times (diagnostic pass outside the timed region; every rank takes part) ----
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    eng = eng_mod.Engine(Xd, F, group=group)
-    for rep in range(2):                             # first repetition warms the allocator
-        t = [ev() for _ in range(6)]
-        t[0].record()
-        eng.stats(w["scale_type"], 1, defer_row_means=True)
-        t[1].record()
-        eng.mark_centre = ev()
-        t_c = eng.mark_centre
-        G = eng.gram()
-        t[2].record()
-        S, V = eng.eig_pod(G)
-        t[3].record()
-        eng.backproject(eng.pod_weights[:, :r].contiguous())
-        t[4].record()
-        eng.qrcp(block=QR_BLOCK)
-        t[5].record()
-        ctx.sync_all()
-    names = ["stats", "gram", "eigh", "backproject", "qrcp"]
-    stages = {nm: ctx.max_over_ranks(t[i].elapsed_time(t[i + 1])) for i, nm in enumerate(names)}
-    if m > 64 and t_c.query():                       # the centred-copy pass (HBM) apart from the Gram kernel (FP64)
-        try:
-            c_ms, g_ms = t[1].elapsed_time(t_c), t_c.elapsed_time(t[2])
-        except RuntimeError:                         # in-kernel centring (no room for the copy): nothing to split
-            c_ms, g_ms = 0.0, stages["gram"]
-        c_ms, g_ms = ctx.max_over_ranks(c_ms), ctx.max_over_ranks(g_ms)
-        if c_ms > 0:
-            stages["centre"], stages["gram"] = c_ms, g_ms
-    del eng, G, S, V
+    # ---- per-stage device times of the TIMED steps themselves (Engine.trace: events around every stage) ----
+    acc = {}
+    for marks_k in step_marks_all:
+        d = {}
+        for nm, m0, m1 in marks_k:
+            if nm == "centre_end":
+                d["_centre_end"] = m0
+            else:
+                d[nm] = (m0, m1)
+        for nm, (m0, m1) in [(k2, v2) for k2, v2 in d.items() if not k2.startswith("_")]:
+            if nm == "gram" and "_centre_end" in d:
+                acc.setdefault("centre", []).append(m0.elapsed_time(d["_centre_end"]))
+                acc.setdefault("gram", []).append(d["_centre_end"].elapsed_time(m1))
+            else:
+                acc.setdefault(nm, []).append(m0.elapsed_time(m1))
+    order = ["stats", "centre", "gram", "eigh", "backproject", "qrcp"]
+    stages = {nm: ctx.max_over_ranks(sum(acc[nm]) / len(acc[nm])) if nm in acc else None for nm in order}
+    stages = {k2: v2 for k2, v2 in stages.items() if v2 is not None}
 
     # ---- rooflines ----
     hbm, fp64 = peaks["hbm_gbs"], peaks["fp64_tflops"]

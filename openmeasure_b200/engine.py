@@ -83,7 +83,27 @@ def tiles_for(n):
     return (int(n) + TB - 1) // TB
 
 
+def _staged(name):
+    """Record CUDA events around a stage when Engine.trace is on (bench.py: per-stage device times of the TIMED
+    steps themselves, no host synchronisation added)."""
+    def deco(fn):
+        def wrapped(self, *a, **k):
+            if not Engine.trace:
+                return fn(self, *a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(self, *a, **k)
+            e1.record()
+            self.marks.append((name, e0, e1))
+            return out
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 class Engine:
+    trace = False
+
     def __init__(self, X_dev, n_features, group=None, comm=None):
         require_cuda()
         assert X_dev.is_cuda and X_dev.dtype == torch.float64 and X_dev.dim() == 2
@@ -117,6 +137,7 @@ class Engine:
         self.vn = None
         self.r = None
         self.ntiles = tiles_for(self.n_loc)
+        self.marks = []
         self._X0c = None                                 # centred copy of X for the many-snapshot tensor-core passes
 
     # ------------------------------------------------------------------------------------ centred copy
@@ -199,6 +220,7 @@ class Engine:
         return (self.n_c_loc, self.n_c, self.cell0, self.rank, self.world)
 
     # ------------------------------------------------------------------------------------ K1
+    @_staged("stats")
     def stats(self, scale_type="std", axis_cnt=1, defer_row_means=False):
         """Centring vector and per-feature scale (sparse_sensing.py:106-167).  defer_row_means: the
         caller runs gram() next, whose single read of X also yields the row means (m <= 64)."""
@@ -279,6 +301,7 @@ class Engine:
         self.scl[f] = value
 
     # ------------------------------------------------------------------------------------ K3
+    @_staged("gram")
     def gram(self, centred=True, scaled=True):
         """G = X0^T X0 (m x m) from per-feature Grams of the centred rows."""
         self._wait_arrival()
@@ -294,8 +317,10 @@ class Engine:
             # tensor-core Gram on the copy -- no FP64 add left in its inner loop; back-projection reuses the copy
             self._cnt_pending = False
             self._X0c = X0c
-            if getattr(self, "mark_centre", None) is not None:   # bench.py: the centred-copy pass timed on its own
-                self.mark_centre.record()
+            if Engine.trace:                             # bench.py: the centred-copy pass timed on its own
+                ec = torch.cuda.Event(enable_timing=True)
+                ec.record()
+                self.marks.append(("centre_end", ec, ec))
             _lib.call("omb_gram", _p(X0c), F, ncl, m, None, _p(Gf), _p(ws), st)
         elif centred and self._cnt_pending:             # row means + centred Grams from one read of X
             _lib.call("omb_gram_rowmeans", _p(self.X), F, ncl, m, _p(self._cnt), _p(Gf), _p(ws), st)
@@ -308,6 +333,7 @@ class Engine:
             G = self.comm.sum_ordered(G)
         return G
 
+    @_staged("eigh")
     def eig_pod(self, G):
         """m x m eigensolve -> singular values (descending) and right singular vectors (the
         largest-magnitude component of each vector positive)."""
@@ -350,6 +376,7 @@ class Engine:
         return S, V
 
     # ------------------------------------------------------------------------------------ K5
+    @_staged("backproject")
     def backproject(self, W, centred=True, scaled=True, norms=True):
         """Ut (r x ld, mode-major) = (X0 W)^T, plus the initial pivoted-QR norms."""
         self._wait_arrival()
@@ -429,6 +456,7 @@ class Engine:
         self.vn = None      # recomputed by the placement
 
     # ------------------------------------------------------------------------------------ K6
+    @_staged("qrcp")
     def qrcp(self, s=None, block=8):
         """Pivoted QR over the candidate rows; returns (piv, rdiag, gap) as device tensors.
         Multi-rank: piv holds GLOBAL row indices and is identical on every rank."""
