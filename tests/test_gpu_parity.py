@@ -631,10 +631,10 @@ def test_npy_ingest_roundtrip_and_fit(torch_cuda, tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------
-# BASELINE.json's full sizes (configs[1]: 1.65M x 41, r = 40; configs[2]: 16.2M x 256, r = 100, one
-# GPU's worth of HBM): size-independent properties, everything checked on the device
+# BASELINE.json's full sizes (configs[1]: 1.65M x 41, r = 40; configs[2]: 16.2M x 256, r = 100; configs[4]'s
+# snapshot count, 1024, on a quarter of one GPU's shard): size-independent properties, everything checked on the device
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("F,n_c,m,r", [(9, 183620, 41, 40), (9, 1800000, 256, 100)])
+@pytest.mark.parametrize("F,n_c,m,r", [(9, 183620, 41, 40), (9, 1800000, 256, 100), (8, 262144, 1024, 100)])
 def test_full_size_properties(torch_cuda, F, n_c, m, r):
     from openmeasure_b200 import synth as gsynth
     torch = torch_cuda
