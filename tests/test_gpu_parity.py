@@ -520,6 +520,49 @@ def test_gram_and_backprojection_match_numpy(torch_cuda, F, n_c, m, r):
     np.testing.assert_allclose(eng.vn.cpu().numpy()[:F * n_c], np.linalg.norm(Uref, axis=1), rtol=1e-12)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_many_snapshot_kernels_random_shapes(torch_cuda, seed):
+    """The stream-K row slices of the Gram (a CTA's slice may start and end anywhere: in the middle of a tile's rows,
+    across tiles and features, or be empty), ragged last chunks, ragged last column tiles and single-chunk blocks;
+    the centred copy; the 16-row-warp back-projection with every mode-block count -- against numpy."""
+    torch = torch_cuda
+    from openmeasure_b200 import engine as E
+    rng = np.random.default_rng(1000 + seed)
+    F = int(rng.integers(1, 5))
+    m = int(rng.choice([66, 70, 128, 130, 200, 256, 258, 384, 520]))
+    n_c = int(rng.choice([1, 3, 15, 16, 17, 40, 129, 500, 1237, 2900]))
+    r = int(2 * rng.integers(1, min(m, 140) // 2 + 1))
+    X = rng.standard_normal((F * n_c, m)) * 10.0 ** rng.integers(-2, 3, (F * n_c, 1)) + rng.standard_normal((F * n_c, 1))
+    if n_c * m < 2:
+        pytest.skip("degenerate block")
+    eng = E.Engine(torch.from_numpy(X).cuda(), F, group=False)
+    eng.stats("none", 1, defer_row_means=True)
+    G = eng.gram().cpu().numpy()
+    np.testing.assert_array_equal(eng.cnt.cpu().numpy(), np.mean(X, axis=1))
+    X0 = X - np.mean(X, axis=1)[:, None]
+    Gref = X0.T @ X0
+    np.testing.assert_allclose(G, Gref, rtol=0, atol=5e-13 * max(np.abs(Gref).max(), 1e-300))
+    np.testing.assert_array_equal(G, G.T)
+    W = rng.standard_normal((m, r))
+    eng.backproject(torch.from_numpy(W).cuda())
+    Uref = X0 @ W
+    np.testing.assert_allclose(eng.basis_rows().cpu().numpy(), Uref, rtol=0, atol=5e-13 * max(np.abs(Uref).max(), 1e-300))
+    np.testing.assert_allclose(eng.vn.cpu().numpy()[:F * n_c], np.linalg.norm(Uref, axis=1), rtol=1e-11, atol=1e-300)
+    # the same without room for the centred copy: in-kernel centring (centring warps / CENTRE = true instantiations)
+    import os
+    os.environ["OMB_CENTRED_COPY"] = "0"
+    try:
+        eng2 = E.Engine(torch.from_numpy(X).cuda(), F, group=False)
+        eng2.stats("none", 1, defer_row_means=True)
+        G2 = eng2.gram().cpu().numpy()
+        eng2.backproject(torch.from_numpy(W).cuda())
+        U2 = eng2.basis_rows().cpu().numpy()
+    finally:
+        del os.environ["OMB_CENTRED_COPY"]
+    np.testing.assert_allclose(G2, Gref, rtol=0, atol=5e-13 * max(np.abs(Gref).max(), 1e-300))
+    np.testing.assert_allclose(U2, Uref, rtol=0, atol=5e-13 * max(np.abs(Uref).max(), 1e-300))
+
+
 # ---------------------------------------------------------------------------------------------
 # GEM placement (SURVEY 8f row 1): the reference's own selections (golden g6/g7, jitter reproduced
 # by seeding numpy like the fixture generator) and the oracle on a larger case
