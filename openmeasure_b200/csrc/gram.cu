@@ -3,8 +3,9 @@
 // Replaces the O(n m^2) part of np.linalg.svd(X0) (reference sparse_sensing.py:272, LAPACK dgesdd):
 // per feature block f, Gf = sum_i (x_i - cnt_i)(x_i - cnt_i)^T over the block's rows, so the
 // scaling 1/scl_f^2 (known only after the statistics pass) is applied to the tiny m x m result
-// and X0 is never materialised.  DMMA.8x8x4 (mma.sync m8n8k4 f64) -- tcgen05 has no FP64 kind.
-// Deterministic: fixed row split per feature, partial tiles reduced in fixed order, no atomics.
+// and the scaled X0 is never materialised (m > 64: the caller passes the centred copy X - cnt and cnt = NULL, so
+// that the inner loops hold no FP64 add).  DMMA.8x8x4 (mma.sync m8n8k4 f64) -- tcgen05 has no FP64 kind.
+// Deterministic: fixed work decomposition per (F, n_c, m, SM count), partial tiles reduced in fixed order, no atomics.
 #include <stdlib.h>
 #include "common.cuh"
 #include "../../include/omb200.h"

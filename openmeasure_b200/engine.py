@@ -10,6 +10,8 @@ Data layout in HBM (FP64 throughout):
     scl    (F,)             scale per feature block         (reference X_scl[f * n_points, 0])
     Ut     (ntiles, r, 128) tiled mode-major basis, Ut[i // 128, q, i % 128] = U_r[i, q]
     work   (ntiles, r, 128) trailing matrix of the pivoted QR
+    X0c    like X           X - cnt, m > 64 only: the centred copy the FP64 tensor-core passes read (a DADD in their
+                            inner loop shares the pipe with DMMA); from the Gram pass to the back-projection, pooled
 With torch.distributed initialised, every rank holds the cells [c0, c0 + n_c_loc) of EVERY
 feature; only F*4 statistics, the m x m Gram and (per pivot step) one small record cross NVLink.
 """
