@@ -1179,3 +1179,32 @@ def test_unchanged_constructor_drives_several_devices(torch_cuda, monkeypatch):
     assert Cg.shape == (6, F * n_c) and mask[Cg.pivots].all()
     with pytest.raises(ValueError):
         spr.fit(select_modes='bogus')
+
+
+def test_config3_snapshot_and_sensor_counts_match_oracle(torch_cuda):
+    """configs[2]'s m = 256 snapshots and r = s = 100 sensors on 1/90 of its rows (9 x 20 000 cells): every stage of the
+    many-snapshot route against the oracle (= the reference's np.linalg.svd and scipy.linalg.qr calls, ~10 s of CPU)."""
+    from oracle import pod_oracle as po, synth as osynth
+    F, n_c, m, r = 9, 20000, 256, 100
+    X = osynth.snapshots(F, n_c, m, r)
+    ref = po.placement_pipeline(X, F, r)
+    spr = _sps().SPR(X, F, np.zeros((n_c, 3)))
+    spr.fit(select_modes='number', n_modes=r)
+    C = spr.optimal_placement()
+    np.testing.assert_array_equal(spr.X_cnt, ref["X_cnt"])
+    np.testing.assert_array_equal(spr.X_scl, ref["X_scl"])
+    np.testing.assert_allclose(spr.Sigma_r, ref["Sigma_r"], rtol=RTOL)
+    np.testing.assert_array_equal(spr.qr_pivots, ref["piv"])
+    Ur, sg = _sign_align(spr.Ur, ref["Ur"])
+    np.testing.assert_allclose(Ur[:, :r // 2], ref["Ur"][:, :r // 2], rtol=0, atol=1e-9)
+    spr.train(C)
+    ys = []
+    for j in (0, 100, 255):
+        y = np.zeros((r, 3))
+        y[:, 0] = X[ref["piv"], j]
+        y[:, 2] = ref["piv"] // n_c
+        ys.append(y)
+    a, _ = spr.predict(ys)
+    Co = po.one_hot(ref["piv"], X.shape[0])
+    ao, _ = po.predict_ols(po.theta(Co, ref["Ur"]), ys, Co, ref["X_cnt"], ref["X_scl"], n_c)
+    np.testing.assert_allclose(spr.reconstruct(a), po.reconstruct(ref["Ur"], ao, ref["X_cnt"], ref["X_scl"]), rtol=1e-9)
