@@ -588,6 +588,7 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
     else:
         res["e2e"] = None
     del Xd
+    eng_mod.release_scratch()                        # the pooled centred-copy buffer of this workload
     torch.cuda.empty_cache()
     if brief:
         for k in ("step_ms",):
@@ -775,6 +776,8 @@ def run_reconstruct(ctx, w, peaks):
         except Exception as e:
             cpu = {"error": repr(e)}
     del spr, C, Xd
+    from openmeasure_b200 import engine as eng_mod
+    eng_mod.release_scratch()
     torch.cuda.empty_cache()
     return {"workload": RECON["name"], "rows": F * n_c, "modes": r, "sensors": s, "device_resident": dev, "e2e": e2e,
             "cpu_baseline": cpu}
