@@ -549,6 +549,11 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
         if ent and ent.get("qr_block") == QR_BLOCK and world == 1:
             traffic = ent["qr_passes"]["dram_bytes_per_launch"]
             tsrc = "profiles/r02_traffic.json (ncu dram__bytes_read+write per pass launch, same command)"
+            for nm, t_ent in (ent.get("stages") or {}).items():      # measured DRAM bytes of the other stages' kernels
+                if nm in st_roof:
+                    st_roof[nm]["traffic"] = t_ent["dram_bytes_per_step"]
+            if "qrcp" in st_roof:
+                st_roof["qrcp"]["traffic"] = ent["qr_passes"]["dram_bytes_per_step"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
