@@ -69,6 +69,11 @@ int omb_row_means(const double* d_X, int64_t rows, int64_t m, double* d_cnt, voi
  * 16-byte aligned. */
 int omb_center_rows(const double* d_X, int64_t rows, int64_t m, int compute_means, double* d_cnt,
                     double* d_X0c, void* stream);
+/* The same with a padded row pitch ld_out >= m (columns m .. ld_out-1 written as zeros) and any m: an odd snapshot
+ * count gets an even pitch, so that the tensor-core kernels (16-byte aligned rows) serve it too -- a zero snapshot
+ * changes neither the Gram of the first m columns nor the back-projection. */
+int omb_center_rows_padded(const double* d_X, int64_t rows, int64_t m, int64_t ld_out, int compute_means,
+                           double* d_cnt, double* d_X0c, void* stream);
 /* Per-feature block reductions with numpy's pairwise tree over the n_c*m contiguous elements:
  *   mode 0: d_out[f*4 + {0,1,2}] = {sum, min, max}
  *   mode 1: d_out[f*4 + 3]       = sum((x - d_out[f*4+0]/mean_count)^2)   (np.std's second pass;
@@ -236,6 +241,9 @@ int omb_csr_times_basis(const int64_t* d_indptr, const int64_t* d_indices, const
 int omb_gather_rows(const double* d_Ut, int64_t r, const int64_t* d_piv, int64_t s,
                     double* d_Theta, const double* d_cnt, double* d_cnt_s, void* stream);
 /* Ur (n x r, C-order) <- Ut, and back (for the .Ur attribute / fit(basis=...) / mask) */
+/* d_dst (tiled, r_dst modes) = the first r_dst modes of d_src (tiled, r_src modes): drops the zero padding mode an
+ * odd mode count is back-projected with (U[:, :r], sparse_sensing.py:336) */
+int omb_copy_modes(const double* d_src, int64_t r_src, double* d_dst, int64_t r_dst, int64_t n, void* stream);
 int omb_modes_to_rows(const double* d_Ut, int64_t n, int64_t r, double* d_Ur, void* stream);
 int omb_rows_to_modes(const double* d_Ur, int64_t n, int64_t r, double* d_Ut, double* d_vn,
                       void* stream);

@@ -19,6 +19,8 @@ SIGNATURES = {
     "omb_synth_fill": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _vp, _vp, _dbl, _vp, _vp]),
     "omb_row_means": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "omb_center_rows": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    "omb_center_rows_padded": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),
+    "omb_copy_modes": (_int, [_vp, _i64, _vp, _i64, _i64, _vp]),
     "omb_block_stats_ws_bytes": (_i64, [_i64, _i64]),
     "omb_block_stats": (_int, [_vp, _i64, _i64, _int, _i64, _vp, _vp, _vp]),
     "omb_finalize_scale": (_int, [_vp, _i64, _i64, _int, _vp, _int, _vp, _i64, _vp]),

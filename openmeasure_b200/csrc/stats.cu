@@ -561,6 +561,31 @@ extern "C" int omb_row_means(const double* d_X, int64_t rows, int64_t m, double*
     return check_launch("row_means_kernel");
 }
 
+// X0c[i][j] = X[i][j] - cnt[i] for j < m, 0 for m <= j < ld: the centred copy with an EVEN row pitch for an odd
+// snapshot count (the tensor-core kernels need 16-byte aligned rows; a zero snapshot changes neither the Gram of the
+// first m columns nor the back-projection)
+__global__ void __launch_bounds__(256)
+center_pad_kernel(const double* __restrict__ X, int64_t rows, int64_t m, int64_t ld, const double* __restrict__ cnt,
+                  double* __restrict__ X0c)
+{
+    const int64_t total = rows * ld;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / ld, j = e - row * ld;
+        X0c[e] = j < m ? X[row * m + j] - cnt[row] : 0.0;
+    }
+}
+
+// dst[tile][q][128] = src[tile][q][128] for q < r_dst (r_dst <= r_src): drops the zero padding mode(s) of a basis
+__global__ void __launch_bounds__(256)
+copy_modes_kernel(const double* __restrict__ src, int r_src, double* __restrict__ dst, int r_dst, int64_t ntiles)
+{
+    const int64_t per = (int64_t)r_dst * OMB_TB / 2, total = ntiles * per;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tile = e / per, k = e - tile * per;
+        stg_stream2(dst + tile * ((int64_t)r_dst * OMB_TB) + 2 * k, ldg_stream2(src + tile * ((int64_t)r_src * OMB_TB) + 2 * k));
+    }
+}
+
 static int center_given(const double* d_X, int64_t rows, int64_t m, const double* d_cnt, double* d_X0c, cudaStream_t st)
 {
     int64_t g = ceil_div(rows * (m >> 1), 256);
@@ -684,4 +709,34 @@ extern "C" int omb_scale_rows(const double* d_X, int64_t F, int64_t n_c, int64_t
     dim3 grid((unsigned)gx, (unsigned)F);
     scale_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, n_c, m, d_cnt, d_scl, d_X0);
     return check_launch("scale_rows_kernel");
+}
+
+extern "C" int omb_center_rows_padded(const double* d_X, int64_t rows, int64_t m, int64_t ld_out, int compute_means,
+                                      double* d_cnt, double* d_X0c, void* stream)
+{
+    OMB_CHECK_ARG(d_X && d_cnt && d_X0c, "null pointer");
+    OMB_CHECK_ARG(rows > 0 && m > 0 && ld_out >= m, "bad size");
+    if (ld_out == m && (m & 1) == 0 && ((reinterpret_cast<uintptr_t>(d_X) | reinterpret_cast<uintptr_t>(d_X0c)) & 15) == 0)
+        return omb_center_rows(d_X, rows, m, compute_means, d_cnt, d_X0c, stream);
+    if (compute_means) {
+        int rc = omb_row_means(d_X, rows, m, d_cnt, stream);
+        if (rc) return rc;
+    }
+    int64_t g = ceil_div(rows * ld_out, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    center_pad_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_X, rows, m, ld_out, d_cnt, d_X0c);
+    return check_launch("center_pad_kernel");
+}
+
+extern "C" int omb_copy_modes(const double* d_src, int64_t r_src, double* d_dst, int64_t r_dst, int64_t n, void* stream)
+{
+    OMB_CHECK_ARG(d_src && d_dst, "null pointer");
+    OMB_CHECK_ARG(n > 0 && r_dst > 0 && r_dst <= r_src, "bad size");
+    const int64_t ntiles = basis_tiles(n);
+    int64_t g = ceil_div(ntiles * r_dst * (OMB_TB / 2), 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    copy_modes_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_src, (int)r_src, d_dst, (int)r_dst, ntiles);
+    return check_launch("copy_modes_kernel");
 }

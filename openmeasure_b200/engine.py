@@ -147,19 +147,21 @@ class Engine:
         """m > 64 (the DMMA-bound kernels), even m, aligned X, and room for a second copy of X next to the basis
         and the placement workspace.  OMB_CENTRED_COPY=0 forces the in-kernel centring path."""
         import os
-        if self.m <= 64 or (self.m & 1) or (self.X.data_ptr() & 15) or os.environ.get("OMB_CENTRED_COPY", "1") == "0":
+        if self.m <= 64 or os.environ.get("OMB_CENTRED_COPY", "1") == "0":
             return False
+        mp = self.m + (self.m & 1)                       # an odd snapshot count gets an even row pitch (a zero snapshot)
         pooled = _SCRATCH_POOL.get(self.dev)
-        if pooled is not None and pooled.numel() >= 8 * self.n_loc * self.m:
+        if pooled is not None and pooled.numel() >= 8 * self.n_loc * mp:
             return True
         free, _ = torch.cuda.mem_get_info(self.dev)
         free += torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
-        need = 8 * self.n_loc * self.m
+        need = 8 * self.n_loc * mp
         return free - need >= 16 * self.n_loc * min(self.m, 128) + (1 << 30)
 
     def _new_centred(self):
         """Uninitialised buffer shaped like X from the scratch pool (or the allocator); None when out of memory."""
-        nbytes = 8 * self.n_loc * self.m
+        mp = self.m + (self.m & 1)
+        nbytes = 8 * self.n_loc * mp
         buf = _scratch_take(self.dev, nbytes)
         if buf is None:
             try:
@@ -167,7 +169,7 @@ class Engine:
             except torch.OutOfMemoryError:
                 return None
         self._X0c_buf = buf
-        return buf[:nbytes].view(torch.float64).view(self.n_loc, self.m)
+        return buf[:nbytes].view(torch.float64).view(self.n_loc, mp)
 
     def _drop_centred(self):
         """The centred copy's last reader has been queued on the current stream: hand the buffer on."""
@@ -182,8 +184,20 @@ class Engine:
             out = self._new_centred()
             if out is None:
                 return None
-        _lib.call("omb_center_rows", _p(X), int(X.shape[0]), self.m, 1 if compute_means else 0, _p(cnt), _p(out), _stream())
+        _lib.call("omb_center_rows_padded", _p(X), int(X.shape[0]), self.m, int(out.shape[1]), 1 if compute_means else 0,
+                  _p(cnt), _p(out), _stream())
         return out
+
+    def _gram_of_copy(self, X0c, F, ncl, Gf_out):
+        """Per-feature Grams of a centred copy (row pitch mp >= m) into Gf_out (F * m * m)."""
+        m, mp = self.m, int(X0c.shape[1])
+        ws = _ws(_lib.load().omb_gram_ws_bytes(F, ncl, mp), self.dev)
+        if mp == m:
+            _lib.call("omb_gram", _p(X0c), F, ncl, m, None, _p(Gf_out), _p(ws), _stream())
+            return
+        Gp = torch.empty(F * mp * mp, dtype=torch.float64, device=self.dev)
+        _lib.call("omb_gram", _p(X0c), F, ncl, mp, None, _p(Gp), _p(ws), _stream())
+        Gf_out.view(F, m, m).copy_(Gp.view(F, mp, mp)[:, :m, :m])      # drop the zero snapshot
 
     def check_p2p(self):
         """Raise if a peer never answered during a peer-memory exchange since the last check (the pivot
@@ -264,7 +278,7 @@ class Engine:
                 if fuse_gram and X0c is not None:
                     X0f = X0c[f * ncl:(f + 1) * ncl]
                     self._centre(Xf, cf, True, out=X0f)
-                    _lib.call("omb_gram", _p(X0f), 1, ncl, m, None, _p(Gf[f * m * m:(f + 1) * m * m]), _p(gws), st)
+                    self._gram_of_copy(X0f, 1, ncl, Gf[f * m * m:(f + 1) * m * m])
                 elif fuse_gram:
                     _lib.call("omb_gram_rowmeans", _p(Xf), 1, ncl, m, _p(cf), _p(Gf[f * m * m:(f + 1) * m * m]), _p(gws), st)
                 elif axis_cnt == 1:
@@ -323,7 +337,7 @@ class Engine:
                 ec = torch.cuda.Event(enable_timing=True)
                 ec.record()
                 self.marks.append(("centre_end", ec, ec))
-            _lib.call("omb_gram", _p(X0c), F, ncl, m, None, _p(Gf), _p(ws), st)
+            self._gram_of_copy(X0c, F, ncl, Gf)
         elif centred and self._cnt_pending:             # row means + centred Grams from one read of X
             _lib.call("omb_gram_rowmeans", _p(self.X), F, ncl, m, _p(self._cnt), _p(Gf), _p(ws), st)
             self._cnt_pending = False
@@ -387,11 +401,22 @@ class Engine:
         assert m == self.m
         Ut = self._new_basis(r)
         vn = torch.zeros(self.ntiles * TB, dtype=torch.float64, device=self.dev) if norms else None
-        src, cnt = self.X, (self.cnt if centred else None)
+        src, cnt, mk = self.X, (self.cnt if centred else None), self.m
         if centred and self._X0c is not None:           # the centred copy the Gram pass left behind
-            src, cnt = self._X0c, None
-        _lib.call("omb_backproject", _p(src), self.F, self.n_c_loc, self.m, _p(cnt), _p(self.scl if scaled else None),
-                  _p(W), r, _p(Ut), _p(vn), _stream())
+            src, cnt, mk = self._X0c, None, int(self._X0c.shape[1])
+            if mk != m:                                 # odd snapshot count: the copy carries a zero snapshot
+                W = torch.cat([W, torch.zeros(mk - m, r, dtype=torch.float64, device=self.dev)], dim=0).contiguous()
+        if src is self._X0c and (r & 1) and (mk > 64 or r > 64):
+            # odd mode count: back-project one zero mode more (the tensor-core kernel wants even r), then drop it
+            Wp = torch.cat([W, torch.zeros(mk, 1, dtype=torch.float64, device=self.dev)], dim=1).contiguous()
+            Utp = self._new_basis(r + 1)
+            _lib.call("omb_backproject", _p(src), self.F, self.n_c_loc, mk, None, _p(self.scl if scaled else None),
+                      _p(Wp), r + 1, _p(Utp), _p(vn), _stream())
+            _lib.call("omb_copy_modes", _p(Utp), r + 1, _p(Ut), r, self.n_loc, _stream())
+            del Utp
+        else:
+            _lib.call("omb_backproject", _p(src), self.F, self.n_c_loc, mk, _p(cnt), _p(self.scl if scaled else None),
+                      _p(W), r, _p(Ut), _p(vn), _stream())
         self._drop_centred()                            # its last reader has been queued: the memory can be reused
         self.Ut, self.vn, self.r = Ut, vn, r
         return Ut

@@ -520,7 +520,7 @@ def test_gram_and_backprojection_match_numpy(torch_cuda, F, n_c, m, r):
     np.testing.assert_allclose(eng.vn.cpu().numpy()[:F * n_c], np.linalg.norm(Uref, axis=1), rtol=1e-12)
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(36))
 def test_many_snapshot_kernels_random_shapes(torch_cuda, seed):
     """The stream-K row slices of the Gram (a CTA's slice may start and end anywhere: in the middle of a tile's rows,
     across tiles and features, or be empty), ragged last chunks, ragged last column tiles and single-chunk blocks;
@@ -529,9 +529,9 @@ def test_many_snapshot_kernels_random_shapes(torch_cuda, seed):
     from openmeasure_b200 import engine as E
     rng = np.random.default_rng(1000 + seed)
     F = int(rng.integers(1, 5))
-    m = int(rng.choice([66, 70, 128, 130, 200, 256, 258, 384, 520]))
+    m = int(rng.choice([66, 70, 128, 130, 200, 256, 258, 384, 520, 67, 129, 257, 301]))     # odd counts: padded copy
     n_c = int(rng.choice([1, 3, 15, 16, 17, 40, 129, 500, 1237, 2900]))
-    r = int(2 * rng.integers(1, min(m, 140) // 2 + 1))
+    r = int(rng.integers(1, min(m, 140) + 1)) if seed % 3 == 0 else int(2 * rng.integers(1, min(m, 140) // 2 + 1))
     X = rng.standard_normal((F * n_c, m)) * 10.0 ** rng.integers(-2, 3, (F * n_c, 1)) + rng.standard_normal((F * n_c, 1))
     if n_c * m < 2:
         pytest.skip("degenerate block")
