@@ -212,24 +212,31 @@ class Clocks:
 # ------------------------------------------------------------------------------------------------
 # algorithmic work per stage; QR: bytes of the schedule omb_qrcp actually executes
 # ------------------------------------------------------------------------------------------------
-def qrcp_schedule_bytes(n, r, s, block):
+def qrcp_schedule_bytes(n, r, s, block, stats=None):
     """(bytes, launches) of the pass kernels: read-only GEMV passes read L rows, block-closing
-    apply passes read L rows and write L-t-1; every pass reads vn1/vn2 and writes vn1."""
+    apply passes read L rows and write L-t-1; every pass reads vn1/vn2 and writes vn1.
+    stats (Engine.qr_stats() of a run with lazy norm down-dates): the read-only passes are charged
+    what they VISITED -- 512 bytes per (64-candidate segment, row) and 64 x 24 bytes of norms per
+    segment visit, counted by the kernels themselves -- instead of every row of every column."""
+    lazy = bool(stats and stats.get("lazy"))
     total, launches = 8 * n, 1            # step-0 argmax pass reads vn1
     i0 = 0
     for i in range(s - 1):
         t, L = i - i0, r - i0
-        total += 8 * n * L + 24 * n
         launches += 1
         if t == block - 1:
-            total += 8 * n * (L - t - 1)
+            total += 8 * n * L + 24 * n + 8 * n * (L - t - 1)
             i0 = i + 1
+        elif not lazy:
+            total += 8 * n * L + 24 * n
+    if lazy:
+        total += 512 * int(stats["seg_rows"]) + 64 * 24 * int(stats["seg_visits"])
     return total, launches
 
 
-def stage_rooflines(n_loc, m, r, stages_ms, step_ms, hbm_gbs, fp64_tflops, peak_src):
+def stage_rooflines(n_loc, m, r, stages_ms, step_ms, hbm_gbs, fp64_tflops, peak_src, qr_stats=None):
     """One roofline entry per stage, per GPU (n_loc rows), on ALGORITHMIC work, plus the composite."""
-    qbytes, qlaunch = qrcp_schedule_bytes(n_loc, r, r, QR_BLOCK)
+    qbytes, qlaunch = qrcp_schedule_bytes(n_loc, r, r, QR_BLOCK, qr_stats)
     gram_flop = float(n_loc) * m * (m + 1)
     gram_bytes = 8.0 * n_loc * m + 8.0 * n_loc
     bp_flop = 2.0 * n_loc * m * r
@@ -539,14 +546,26 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
     # ---- rooflines ----
     hbm, fp64 = peaks["hbm_gbs"], peaks["fp64_tflops"]
     n_max = F * shard_cells(n_c, world, 0)[1]          # the largest shard bounds the step
-    st_roof, comp, qbytes, qlaunch = stage_rooflines(n_max, m, r, stages, ms_per_step, hbm, fp64, peaks)
+    # the read-only QR passes report what they visited (lazy norm down-dates); the largest count bounds the step
+    qst = spr._eng.qr_stats() or {"seg_rows": 0, "seg_visits": 0, "retries": 0, "lazy": False}
+    qst = {"seg_rows": int(ctx.max_over_ranks(float(qst["seg_rows"]))), "seg_visits": int(ctx.max_over_ranks(float(qst["seg_visits"]))),
+           "retries": int(qst["retries"]), "lazy": bool(qst["lazy"])}
+    st_roof, comp, qbytes, qlaunch = stage_rooflines(n_max, m, r, stages, ms_per_step, hbm, fp64, peaks, qst)
+    qbytes_eager, _ = qrcp_schedule_bytes(n_max, r, r, QR_BLOCK)
+    qr_lazy = {"on": qst["lazy"], "alpha": float(L.omb_qrcp_set_lazy(-1.0)), "catch_up_rounds": qst["retries"],
+               "read_only_pass_bytes": 512 * qst["seg_rows"] + 1536 * qst["seg_visits"],
+               "eager_schedule_bytes_per_step": qbytes_eager, "executed_over_eager": qbytes / qbytes_eager,
+               "note": "partial column norms only shrink: segments of 64 candidates whose largest norm at a block start is "
+                       "below alpha x the pivot norm sit the block's read-only passes out (exact; pivots are those of the "
+                       "eager schedule, parity-tested); bytes counted by the kernels"}
+    L.omb_qrcp_set_lazy(qr_lazy["alpha"])
     qr_avg = ctx.max_over_ranks(sum(qr_ms) / max(len(qr_ms), 1))
     achieved = qbytes / (qr_avg * 1e-3) / 1e9 if qr_avg > 0 else 0.0
     traffic, tsrc = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tj.get(w["key"])
-        if ent and ent.get("qr_block") == QR_BLOCK and world == 1:
+        if ent and ent.get("qr_block") == QR_BLOCK and world == 1 and bool(ent.get("qr_lazy")) == qst["lazy"]:
             traffic = ent["qr_passes"]["dram_bytes_per_launch"]
             tsrc = "profiles/r02_traffic.json (ncu dram__bytes_read+write per pass launch, same command)"
             for nm, t_ent in (ent.get("stages") or {}).items():      # measured DRAM bytes of the other stages' kernels
@@ -563,8 +582,9 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
                 "algorithmic_bytes_per_launch": qbytes / qlaunch, "algorithmic_bytes_per_step": qbytes,
                 "launches_per_step": qlaunch, "avg_launch_us": qr_avg * 1e3 / qlaunch, "qrcp_ms_per_step": qr_avg,
                 "peak_source": peaks["hbm_source"],
-                "note": "bytes = schedule actually executed (blocked QRCP), per GPU; time = CUDA events around "
-                        "optimal_placement in the timed steps, incl. the 1-CTA panel kernels",
+                "note": "bytes = schedule actually executed (blocked QRCP with lazy norm down-dates: see `lazy`), per GPU; "
+                        "time = CUDA events around optimal_placement in the timed steps, incl. the 1-CTA panel kernels",
+                "lazy": qr_lazy,
                 "stages": st_roof, "composite": comp,
                 "fp64_peak": {"tflops": fp64, "source": peaks["fp64_source"]}}
 

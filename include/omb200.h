@@ -143,6 +143,19 @@ int omb_backproject(const double* d_X, int64_t F, int64_t n_c, int64_t m, const 
  * meter).  optimal_placement(mask=...) zeroes the excluded rows of the basis beforehand, exactly
  * like the reference (:737-738).  One placement at a time per device. */
 int64_t omb_qrcp_ws_bytes(int64_t n, int64_t r);
+/* Lazy norm down-dates of the blocked schedule (block > 1; omb_qrcp and omb_qrcp_p2p).  dlaqp2's partial
+ * norms only ever shrink, so a candidate whose norm at a block start is below the norm of the pivot that
+ * is finally chosen cannot be that pivot: segments of 64 candidates whose largest norm is below
+ * alpha * (pivot norm at the block start) sit the block's read-only passes out and take their down-dates
+ * in the block-closing pass, which reads them anyway.  A pivot is accepted only if its norm reaches the
+ * bound; otherwise the skipped segments that could beat it are brought up to date first (decided on the
+ * device) -- the pivots are those of the eager schedule.  alpha in (0, 1), 0 = off; returns the previous
+ * value.  Process-wide; default 0.94 or $OMB_QR_LAZY.  Same LAPACK call site (:739). */
+double omb_qrcp_set_lazy(double alpha);
+/* Executed schedule of the last placement on this workspace: out[0] = (segment, row) visits of the
+ * read-only passes (512 bytes each), out[1] = their segment visits (64 x 24 bytes of norms each),
+ * out[2] = catch-up rounds, out[3] = 1 if the lazy scheme was on.  Synchronises the stream. */
+int omb_qrcp_stats(const void* d_ws, int64_t n, int64_t* out, void* stream);
 int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
              void* d_ws, int block, int64_t index_base, int64_t* d_piv, double* d_rdiag,
              double* d_gap, void* stream);

@@ -34,6 +34,8 @@ SIGNATURES = {
     "omb_eigh_jacobi": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "omb_backproject": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "omb_qrcp_ws_bytes": (_i64, [_i64, _i64]),
+    "omb_qrcp_set_lazy": (_dbl, [_dbl]),
+    "omb_qrcp_stats": (_int, [_vp, _i64, _vp, _vp]),
     "omb_qrcp": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "omb_qrcp_record_doubles": (_i64, []),
     "omb_qrcp_mr_start": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),

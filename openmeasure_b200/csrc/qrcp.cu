@@ -16,13 +16,31 @@
 //                          norm down-date (tol3z guard, exact recomputation) + next argmax: the
 //                          trailing matrix is streamed once and never written.
 //                          last step of a block: apply the block's reflectors to every column,
-//                          write the rows below the block, down-date, argmax.
+//                          write the rows below the block, norms (block > 1: exact), argmax.
 //                            block == 1: dlarf arithmetic in registers, the very fma sequence of
 //                                        oracle/csrc/oracle.c -> bit-identical to dlaqp2;
 //                            block  > 1: compact WY on the FP64 tensor path (DMMA.8x8x4).
 //
 // block > 1 moves ~ (1 + 1/block)/2 of the bytes of the unblocked algorithm; pivots are identical
 // on non-degenerate inputs (the degeneracy meter d_gap reports how close any decision was).
+//
+// Lazy norm down-dates (block > 1, omb_qrcp_set_lazy): partial column norms only ever shrink, so a
+// column whose norm at the block start is below the norm of the pivot that is finally chosen cannot
+// be that pivot -- its row of R and its down-date are not needed until the block closes.  Candidates
+// are grouped in SEGMENTS of 64 (half a tile, one warp iteration of the read-only pass).  At a block
+// start every norm is exact and seg_max[seg] holds the segment's largest; the panel sets the bound
+// theta = alpha * (pivot norm) and the in-block passes skip every segment with seg_max < theta.  A
+// pivot found among the remaining segments is THE pivot iff its norm is >= theta (everything skipped
+// is strictly below theta).  Otherwise (norm c < theta) the panel raises `retry`: a catch-up pass
+// brings the skipped segments with seg_max >= c up to date (all deferred steps of the block, same
+// q . a arithmetic as the regular pass), they stay active for the rest of the block, theta drops to
+// c and the panel is repeated on both record sets -- exact again, since what is still skipped is
+// below c.  The block-closing apply pass reads every column anyway and leaves EVERY column's exact
+// trailing norm (sum of squares of the rows it is about to write; dlaqp2's recompute branch taken
+// unconditionally, lazy or not): a norm at a block boundary is a function of the column alone, the
+// in-block down-dates of the visited segments served the block's pivot decisions only.  Lazy and
+// eager runs therefore hold bit-identical norms at every decision, exact ties included.
+// The decisions depend on the data only (identical on every rank of a row-sharded run).
 #include "common.cuh"
 #include <stdlib.h>
 #include "../../include/omb200.h"
@@ -67,10 +85,23 @@ struct Panel {
     double V[QR_BMAX][QR_RMAX];   // in-block reflectors over rows i0.., V[t][k] = 0 (k<t), 1 (k==t)
     double T[QR_BMAX][QR_BMAX];   // compact-WY factor, Q = H_0 ... H_t = I - V T V^T
     double tau[QR_BMAX];
-    double q[QR_RMAX];            // q = Q e_t   ->  R[i, j] = q . A[i0:, j]
+    double qs[QR_BMAX][QR_RMAX];  // q_t = Q e_t of every in-block step  ->  R[i0 + t, j] = q_t . A[i0:, j]
     int64_t posmap[QR_RMAX];      // current LAPACK position of original column c < s
     int64_t col_at_pos[QR_RMAX];  // original column now at position k < s
-    int ncand;                    // argmax records left by the last pass kernel (multi-rank path)
+    int ncand;                    // argmax records left by the last pass kernel
+    int ncand2;                   // ... by the last catch-up pass (records at cand + QR_NCAND / 2)
+    // lazy down-dates (see the file header)
+    int lazy;                     // 0: every pass visits every segment
+    int retry;                    // the last panel could not certify its pivot: catch-up pass + second panel run
+    int xseq;                     // cross-rank exchanges done so far (slot parity and tag of the next one)
+    int nretry;                   // statistics: catch-up rounds of this placement
+    double alpha;                 // theta = alpha * (pivot norm at the block start)
+    double theta;                 // every skipped segment's seg_max is < theta
+    double cstar;                 // exact active maximum that failed the test (the catch-up threshold)
+    long long rest_bits;          // largest block-start norm among the segments still skipped (bit pattern of a
+                                  // double >= 0 or of -1: ordered like a signed integer), for the gap meter
+    unsigned long long seg_rows;  // statistics: (segment, row) visits of the read-only passes
+    unsigned long long seg_visits;// statistics: segment visits of the read-only passes
 };
 
 constexpr int QR_REC = 8 + QR_RMAX;   // doubles per cross-rank record: header + pivot column tail
@@ -178,15 +209,23 @@ qr_norms_kernel(const double* __restrict__ A, int64_t n, int r, double* __restri
 
 __global__ void __launch_bounds__(256)
 qr_init_kernel(const double* __restrict__ vn, int64_t n, double* __restrict__ vn1, double* __restrict__ vn2,
-               Panel* __restrict__ P)
+               Panel* __restrict__ P, double lazy_alpha)
 {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         double v = vn[j];
         vn1[j] = v;
         vn2[j] = v;
     }
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0) {
         for (int k = threadIdx.x; k < QR_RMAX; k += blockDim.x) { P->posmap[k] = k; P->col_at_pos[k] = k; }
+        if (threadIdx.x == 0) {
+            P->ncand = 0; P->ncand2 = 0;
+            P->lazy = lazy_alpha > 0.0 ? 1 : 0;
+            P->retry = 0; P->xseq = 0; P->nretry = 0;
+            P->alpha = lazy_alpha; P->theta = -1.0; P->cstar = -1.0; P->rest_bits = __double_as_longlong(-1.0);
+            P->seg_rows = 0ull; P->seg_visits = 0ull;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -212,67 +251,190 @@ __device__ __noinline__ double recompute_norm(const double* __restrict__ col, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// read-only pass: R[i, j] = q . A[i0:, j], down-date, argmax.  L = r - i0 rows (0 = argmax only).
-// Two adjacent columns per thread (128-bit loads); 64 threads sweep one tile's contiguous burst.
+// read-only pass: R[i, j] = q . A[i0:, j], down-date, argmax.  L = r - i0 rows.
+// A warp iteration sweeps one SEGMENT = 64 adjacent columns (half a tile): two columns per thread
+// (128-bit loads), the trailing rows of the segment are L runs of 512 bytes, 1 KB apart.
+//   GV_START    argmax only (no rows read); leaves every segment's largest norm in seg_w
+//   GV_PASS     in-block step t.  Lazy: the first pass of a block (t == 0) decides which segments the
+//               block skips (seg_r[seg] < theta), clears seg_w for the block-closing apply pass; the
+//               later passes follow the flags
+//   GV_CATCHUP  only after a panel raised `retry` (exits at once otherwise): the skipped segments
+//               with seg_r[seg] >= cstar get the down-dates of steps 0 .. t-1 and become active
+// Each lane first looks at the flags of 32 upcoming segments of its warp (one load instead of a
+// dependent load per iteration), the warp then walks the set bits.
 // ---------------------------------------------------------------------------------------------
 constexpr int GV_THREADS = 256;
+constexpr int GV_WARPS = GV_THREADS / 32;
+constexpr int QR_SEG = 64;        // candidates per segment
+enum { GV_START = 0, GV_PASS = 1, GV_CATCHUP = 2 };
 
-__global__ void __launch_bounds__(GV_THREADS)
-qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, int t, int last_row,
-               const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-               int64_t s_total, Shard sh, Cand* __restrict__ cand)
+template <int MODE>
+__global__ void __launch_bounds__(GV_THREADS, 3)
+qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, int t,
+               Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
+               int64_t s_total, Shard sh, Cand* __restrict__ cand, const double* __restrict__ seg_r,
+               double* __restrict__ seg_w, unsigned char* __restrict__ seg_skip)
 {
-    __shared__ double s_q[QR_RMAX];
-    __shared__ Cand s_c[GV_THREADS / 32];
+    // steps whose row of R this launch forms: the pass does step t, the catch-up steps 0 .. t-1
+    constexpr int NQ = (MODE == GV_CATCHUP) ? QR_BMAX - 1 : 1;
+    __shared__ double s_q[NQ][QR_RMAX];
+    __shared__ Cand s_c[GV_WARPS];
+    __shared__ unsigned long long s_vis;
+    __shared__ long long s_rest;
     pdl_enter();
-    for (int k = threadIdx.x; k < L; k += GV_THREADS) s_q[k] = P->q[k];
+    const bool lazy = (MODE != GV_START) && P->lazy != 0;
+    if (MODE == GV_CATCHUP && (!lazy || P->retry == 0)) return;
+    const int t_lo = (MODE == GV_CATCHUP) ? 0 : t;
+    const int nq = (MODE == GV_CATCHUP) ? t : 1;
+    if (MODE != GV_START)
+        for (int a = 0; a < nq; ++a)
+            for (int k = threadIdx.x; k < L; k += GV_THREADS) s_q[a][k] = P->qs[t_lo + a][k];
+    if (threadIdx.x == 0) { s_vis = 0ull; s_rest = __double_as_longlong(-1.0); }
+    const double theta = lazy ? P->theta : -1.0;
+    const double cstar = lazy ? P->cstar : -1.0;
     __syncthreads();
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Cand best = cand_empty();
-    const int64_t npairs = basis_tiles(n) * (OMB_TB / 2);
-    for (int64_t pr = (int64_t)blockIdx.x * GV_THREADS + threadIdx.x; pr < npairs;
-         pr += (int64_t)gridDim.x * GV_THREADS) {
-        const int64_t j = pr * 2;
-        if (j >= n) continue;
-        double y0 = 0.0, y1 = 0.0;
-        const double* col = src + basis_index(i0, j, r);
-        // n is padded to whole tiles in the norm arrays, so the pair load is always in bounds
-        const double2 pv1 = *reinterpret_cast<const double2*>(vn1 + j);
-        const double2 pv2 = *reinterpret_cast<const double2*>(vn2 + j);
-        int k = 0;
-        for (; k + 8 <= L; k += 8) {
-            double2 a[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = ldg_stream2(col + (int64_t)(k + u) * OMB_TB);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { y0 = fma(s_q[k + u], a[u].x, y0); y1 = fma(s_q[k + u], a[u].y, y1); }
-        }
-        for (; k < L; ++k) {
-            double2 a = ldg_stream2(col + (int64_t)k * OMB_TB);
-            y0 = fma(s_q[k], a.x, y0);
-            y1 = fma(s_q[k], a.y, y1);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int64_t jj = j + e;
-            if (jj >= n) break;
-            double v1 = e ? pv1.y : pv1.x;
-            if (v1 < 0.0) continue;                 // already a pivot
-            if (v1 != 0.0 && L > 0) {
-                const double v2 = e ? pv2.y : pv2.x;
-                if (downdate(e ? y1 : y0, v1, v2)) {
-                    v1 = last_row ? 0.0 : recompute_norm(col + e, L, t, &P->V[0][0], P->tau);
-                    vn2[jj] = v1;
+    const int64_t nseg = basis_tiles(n) * (OMB_TB / QR_SEG);
+    const int64_t wstride = (int64_t)gridDim.x * GV_WARPS;
+    unsigned visits = 0;
+    double rest = -1.0;            // largest block-start norm among the segments this lane leaves skipped
+    for (int64_t base = (int64_t)blockIdx.x * GV_WARPS + warp; base < nseg; base += 32 * wstride) {
+        const int64_t myseg = base + (int64_t)lane * wstride;
+        bool act = myseg < nseg;
+        if (lazy && act) {
+            if (MODE == GV_CATCHUP) {
+                act = false;
+                if (seg_skip[myseg] != 0) {
+                    const double sm = seg_r[myseg];
+                    act = sm >= cstar;
+                    if (act) seg_skip[myseg] = 0;
+                    else rest = dmax(rest, sm);
                 }
-                vn1[jj] = v1;
+            } else if (t == 0) {
+                const double sm = seg_r[myseg];
+                const bool skip = sm < theta;
+                seg_skip[myseg] = skip ? 1 : 0;
+                seg_w[myseg] = -1.0;
+                act = !skip;
+                if (skip) rest = dmax(rest, sm);
+            } else {
+                act = seg_skip[myseg] == 0;
+                if (!act) rest = dmax(rest, seg_r[myseg]);
             }
-            cand_push_lazy(best, v1, jj, sh, P, s_total);
+        }
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, act);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t seg = base + (int64_t)l * wstride;
+            const int64_t j = seg * QR_SEG + 2 * lane;
+            ++visits;
+            if (MODE == GV_START) {
+                double m0 = -1.0;
+                if (j < n) {
+                    const double2 pv1 = *reinterpret_cast<const double2*>(vn1 + j);
+                    if (pv1.x >= 0.0) { m0 = pv1.x; cand_push_lazy(best, pv1.x, j, sh, P, s_total); }
+                    if (j + 1 < n && pv1.y >= 0.0) { m0 = dmax(m0, pv1.y); cand_push_lazy(best, pv1.y, j + 1, sh, P, s_total); }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m0 = dmax(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, o));
+                if (lane == 0) seg_w[seg] = m0;
+                continue;
+            }
+            if (j >= n) continue;
+            const double* col = src + basis_index(i0, j, r);
+            // n is padded to whole tiles in the norm arrays, so the pair load is always in bounds
+            const double2 pv1 = *reinterpret_cast<const double2*>(vn1 + j);
+            const double2 pv2 = *reinterpret_cast<const double2*>(vn2 + j);
+            if (MODE == GV_PASS) {
+                const bool last_row = (t + 1 == L);
+                double y0 = 0.0, y1 = 0.0;
+                int k = 0;
+                for (; k + 8 <= L; k += 8) {
+                    double2 a[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = ldg_stream2(col + (int64_t)(k + u) * OMB_TB);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { y0 = fma(s_q[0][k + u], a[u].x, y0); y1 = fma(s_q[0][k + u], a[u].y, y1); }
+                }
+                for (; k < L; ++k) {
+                    double2 a = ldg_stream2(col + (int64_t)k * OMB_TB);
+                    y0 = fma(s_q[0][k], a.x, y0);
+                    y1 = fma(s_q[0][k], a.y, y1);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t jj = j + e;
+                    if (jj >= n) break;
+                    double v1 = e ? pv1.y : pv1.x;
+                    if (v1 < 0.0) continue;                 // already a pivot
+                    if (v1 != 0.0) {
+                        const double v2 = e ? pv2.y : pv2.x;
+                        if (downdate(e ? y1 : y0, v1, v2)) {
+                            v1 = last_row ? 0.0 : recompute_norm(col + e, L, t, &P->V[0][0], P->tau);
+                            vn2[jj] = v1;
+                        }
+                        vn1[jj] = v1;
+                    }
+                    cand_push_lazy(best, v1, jj, sh, P, s_total);
+                }
+            } else {
+                // catch-up: the deferred steps one after the other, dlaqp2's down-dates in their order
+                // (rare; the segment's rows come from L2 after the first sweep)
+                double v1[2] = {pv1.x, pv1.y}, v2[2] = {pv2.x, pv2.y};
+                bool w2[2] = {false, false};
+                for (int a = 0; a < nq; ++a) {
+                    double y0 = 0.0, y1 = 0.0;
+                    for (int k = 0; k < L; ++k) {
+                        const double2 x = ldg_stream2(col + (int64_t)k * OMB_TB);
+                        y0 = fma(s_q[a][k], x.x, y0);
+                        y1 = fma(s_q[a][k], x.y, y1);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (j + e >= n || v1[e] <= 0.0) continue;     // past the end, a pivot, or an exact zero
+                        if (downdate(e ? y1 : y0, v1[e], v2[e])) {
+                            v1[e] = (a + 1 == L) ? 0.0 : recompute_norm(col + e, L, a, &P->V[0][0], P->tau);
+                            v2[e] = v1[e];
+                            w2[e] = true;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t jj = j + e;
+                    if (jj >= n || v1[e] < 0.0) continue;
+                    if (w2[e]) vn2[jj] = v2[e];
+                    vn1[jj] = v1[e];
+                    cand_push_lazy(best, v1[e], jj, sh, P, s_total);
+                }
+            }
         }
     }
-    best = cand_block_reduce(best, s_c);
+    best = cand_block_reduce(best, s_c);          // (contains a CTA barrier)
+    if (MODE != GV_START) {
+        if (lazy) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rest = dmax(rest, __shfl_xor_sync(0xFFFFFFFFu, rest, o));
+            if (lane == 0 && rest >= 0.0) atomicMax(&s_rest, __double_as_longlong(rest));
+        }
+        if (lane == 0 && visits) atomicAdd(&s_vis, (unsigned long long)visits);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        cand[blockIdx.x] = best;
-        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
+        if (MODE == GV_CATCHUP) {
+            cand[QR_NCAND / 2 + blockIdx.x] = best;
+            if (blockIdx.x == 0) P->ncand2 = (int)gridDim.x;
+        } else {
+            cand[blockIdx.x] = best;
+            if (blockIdx.x == 0) P->ncand = (int)gridDim.x;
+        }
+        if (MODE != GV_START) {
+            if (s_vis) { atomicAdd(&P->seg_rows, s_vis * (unsigned long long)(L * nq)); atomicAdd(&P->seg_visits, s_vis); }
+            if (lazy && s_rest >= 0) atomicMax(&P->rest_bits, s_rest);
+        }
     }
 }
 
@@ -374,11 +536,11 @@ constexpr int AM_THREADS = 128;
 constexpr int AM_SV = 10;     // row stride of sV  [row][refl]   : (2p*10 + c) distinct mod 16
 constexpr int AM_ST = 10;     // row stride of sT  [refl][refl']
 
-template <int LG, int NG>
+template <int LG, int NG, bool EXACT>
 __global__ void __launch_bounds__(AM_THREADS)
 qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L, int t,
                     const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
-                    int64_t s_total, Shard sh, Cand* __restrict__ cand)
+                    int64_t s_total, Shard sh, Cand* __restrict__ cand, double* __restrict__ seg_w)
 {
     constexpr int LP = LG * 8;                 // padded rows
     constexpr int SVT = LP + 2;                // row stride of sVt [refl][row]: == 2 (mod 8)
@@ -402,8 +564,9 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = lane & 3, cq = lane >> 2;
-    const int tG = t >> 3, tp = (t & 7) >> 1, te = t & 1;
+    const int tp = (t & 7) >> 1;                  // t < 8: the rows of R live in row group 0
     const bool last_row = (t + 1 == L);
+    const bool lazy = P->lazy != 0;
 
     Cand best = cand_empty();
     const int64_t nwt = basis_tiles(n) * (OMB_TB / WT);
@@ -422,7 +585,7 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
             const int64_t j = j0 + 8 * g + cq;
             const bool owner = (p == tp) && (j < n);
             pv1[g] = owner ? vn1[j] : -1.0;
-            pv2[g] = owner ? vn2[j] : 1.0;
+            pv2[g] = (owner && !EXACT) ? vn2[j] : 1.0;
         }
         double c[LG][NG][2];
 #pragma unroll
@@ -478,18 +641,24 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
                 const int row = 8 * G + 2 * p + e;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (G == tG && e == te) rij[g] = c[G][g][e];
+                    if (G == 0 && 2 * p + e == t) rij[g] = c[G][g][e];          // t < 8: row group 0
                     if (row > t && row < L) stg_stream(out + (8 * G + e) * OMB_TB + 8 * g, c[G][g][e]);
                 }
             }
-        // down-date: the lanes holding row t (p == tp) own their column's norms
+        // norms: the lanes holding row t (p == tp) own their column's.  EXACT (the block-closing pass of a
+        // blocked schedule): every column gets its EXACT trailing norm from the registers -- dlaqp2's own
+        // fallback, taken unconditionally, vn2 following as there.  The norms at a block boundary are then
+        // a function of the column alone, whether or not the block's read-only passes visited it (lazy
+        // down-dates), so duplicated candidates stay bit-identical and ties fall as in LAPACK.
+        // !EXACT (a single tall reflector, block == 1): dlaqp2's down-date of row t.
+        double wmax = -1.0;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             const int64_t j = j0 + 8 * g + cq;
             const bool owner = (p == tp) && (j < n);
             double v1 = pv1[g];
             bool redo = false;
-            if (owner && v1 > 0.0) redo = downdate(rij[g], v1, pv2[g]);
+            if (owner && v1 > 0.0) redo = EXACT ? true : downdate(rij[g], v1, pv2[g]);
             if (__any_sync(0xFFFFFFFFu, redo)) {
                 // exact trailing norm: each of the column's 4 lanes sums its rows, then combine
                 double sq = 0.0;
@@ -509,8 +678,17 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
             }
             if (owner && v1 >= 0.0) {
                 vn1[j] = v1;
+                wmax = dmax(wmax, v1);
                 cand_push_lazy(best, v1, j, sh, P, s_total);
             }
+        }
+        if (lazy) {
+            // the segment's largest norm at the start of the next block (norms are >= 0 or -1: their
+            // bit patterns order like signed integers)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = dmax(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+            if (lane == 0)
+                atomicMax(reinterpret_cast<long long*>(seg_w + j0 / QR_SEG), __double_as_longlong(wmax));
         }
     }
     best = cand_block_reduce(best, s_c);
@@ -521,23 +699,31 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
 }
 
 typedef void (*ApplyMmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
-                           int64_t, Shard, Cand*);
+                           int64_t, Shard, Cand*, double*);
 
-// tensor-path apply kernel for L rows (L <= 256); *ng = column groups per warp
-static ApplyMmaFn pick_apply_mma(int L, int* ng)
+// tensor-path apply kernel for L rows (L <= 256); *ng = column groups per warp.  exact: the block-closing
+// pass of a blocked schedule; !exact: block == 1 with more than QR_LREG trailing rows
+static ApplyMmaFn pick_apply_mma(int L, bool exact, int* ng)
 {
     const int lg = (L + 7) / 8;
+    if (!exact) {
+        *ng = lg <= 16 ? 2 : 1;
+        if (lg <= 13) return qr_apply_mma_kernel<13, 2, false>;
+        if (lg <= 16) return qr_apply_mma_kernel<16, 2, false>;
+        if (lg <= 24) return qr_apply_mma_kernel<24, 1, false>;
+        return qr_apply_mma_kernel<32, 1, false>;
+    }
     switch (lg) {
-#define OMB_AM_CASE(LGV, NGV) case LGV: *ng = NGV; return qr_apply_mma_kernel<LGV, NGV>;
+#define OMB_AM_CASE(LGV, NGV) case LGV: *ng = NGV; return qr_apply_mma_kernel<LGV, NGV, true>;
         OMB_AM_CASE(1, 4) OMB_AM_CASE(2, 4) OMB_AM_CASE(3, 4) OMB_AM_CASE(4, 4) OMB_AM_CASE(5, 4) OMB_AM_CASE(6, 4)
         OMB_AM_CASE(7, 4) OMB_AM_CASE(8, 4) OMB_AM_CASE(9, 2) OMB_AM_CASE(10, 2) OMB_AM_CASE(11, 2)
         OMB_AM_CASE(12, 2) OMB_AM_CASE(13, 2) OMB_AM_CASE(14, 2) OMB_AM_CASE(15, 2) OMB_AM_CASE(16, 2)
 #undef OMB_AM_CASE
         default: break;
     }
-    if (lg <= 24) { *ng = 1; return qr_apply_mma_kernel<24, 1>; }
+    if (lg <= 24) { *ng = 1; return qr_apply_mma_kernel<24, 1, true>; }
     *ng = 1;
-    return qr_apply_mma_kernel<32, 1>;
+    return qr_apply_mma_kernel<32, 1, true>;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -684,7 +870,7 @@ qr_local_kernel(const Panel* __restrict__ P, const Cand* __restrict__ cand, cons
 template <bool MULTI>
 __global__ void __launch_bounds__(PN_THREADS)
 qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand, const double* __restrict__ src,
-                int r, int i0, int L, int i, int t, int seq_norm, int64_t s_total, int64_t index_base, Shard sh,
+                int r, int i0, int L, int i, int t, int seq_norm, int phase, int64_t s_total, int64_t index_base, Shard sh,
                 const double* recs, P2P pp, double* __restrict__ vn1, int64_t* __restrict__ piv,
                 double* __restrict__ rdiag, double* __restrict__ gap)
 {
@@ -696,6 +882,13 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
     __shared__ int64_t s_win[4];               // winner: global index, LAPACK key, local column, gap bits
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_enter();
+    // lazy down-dates: phase 0 is the regular panel of step i, phase 1 its repetition after a catch-up
+    // pass (launched after every in-block panel, a no-op unless phase 0 raised `retry`)
+    const bool lazy = P->lazy != 0;
+    if (phase == 1 && (!lazy || P->retry == 0)) return;
+    const double theta = (phase == 1) ? P->cstar : P->theta;   // bound on every skipped candidate's norm
+    double rest = __longlong_as_double(P->rest_bits);          // largest block-start norm still skipped (this rank)
+    const int xseq = P->xseq;
 
     // 0. block state -> shared memory (independent of the pivot: overlaps the argmax reduction)
     for (int a = warp; a < t; a += PN_THREADS / 32)
@@ -726,6 +919,10 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
 #pragma unroll
         for (int u = 0; u < NR; ++u) cand_merge(c, rc[u]);
         for (int e = threadIdx.x + NR * PN_THREADS; e < nc; e += PN_THREADS) cand_merge(c, cand[e]);
+        if (phase == 1) {
+            const int nc2 = P->ncand2;               // the catch-up pass's records
+            for (int e = threadIdx.x; e < nc2; e += PN_THREADS) cand_merge(c, cand[QR_NCAND / 2 + e]);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { Cand b = cand_shfl_xor(c, o); cand_merge(c, b); }
         if (lane == 0) s_c[warp] = c;
@@ -745,8 +942,11 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         //    format, collect the world's headers, pick the winner in rank order (identical decision on
         //    every rank), then collect the winner's column tail
         __shared__ double s_hdr[64][8];
-        const unsigned tag = (unsigned)(pp.epoch * 4096 + i + 1);
-        const int parity = i & 1;
+        // slot parity and tag follow the number of exchanges done (a step that needs a catch-up
+        // exchanges twice): slot x & 1 is reused by exchange x + 2, which a rank can only reach after
+        // every rank has published exchange x + 1, i.e. has finished reading exchange x
+        const unsigned tag = (unsigned)(pp.epoch * 4096 + xseq + 1);
+        const int parity = xseq & 1;
         int64_t* err = p2p_flags(pp.mine, sh.world) + 3 * sh.world;
         __syncthreads();                     // s_x complete
         for (int k = threadIdx.x; k < 8 + L; k += PN_THREADS) {
@@ -756,12 +956,14 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
             else if (k == 2) d = __longlong_as_double(c.key);
             else if (k == 3) d = __longlong_as_double(c.idx >= 0 ? glob_index(c.idx, sh) : -1);
             else if (k == 4) d = __longlong_as_double(c.idx);
+            else if (k == 5) d = rest;
             else if (k >= 8) d = s_x[k - 8];
             ll_publish(pp, sh.world, parity, sh.rank, k, d, tag);
         }
         for (int e = threadIdx.x; e < sh.world * 8; e += PN_THREADS)
             s_hdr[e >> 3][e & 7] = ll_receive(pp, sh.world, parity, e >> 3, e & 7, tag, err);
         __syncthreads();
+        if (threadIdx.x == 0) P->xseq = xseq + 1;
         c = cand_empty();
         p_local = -1;
         int wr = -1;
@@ -769,6 +971,7 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
             Cand b;
             b.best = s_hdr[g][0]; b.second = s_hdr[g][1];
             b.key = __double_as_longlong(s_hdr[g][2]); b.idx = __double_as_longlong(s_hdr[g][3]);
+            rest = dmax(rest, s_hdr[g][5]);
             if (b.idx < 0) continue;
             const bool wins = cand_better(b.best, b.key, c.best, c.key);
             cand_merge(c, b);
@@ -791,6 +994,20 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
         }
         const double* rcw = recs + (int64_t)(wr < 0 ? 0 : wr) * QR_REC + 8;
         for (int k = threadIdx.x; k < L; k += PN_THREADS) s_x[k] = __ldcg(rcw + k);
+    }
+    if (lazy) {
+        // every thread holds the same (global) winner.  Inside a block the candidates of the skipped
+        // segments are all below theta: the winner is certified iff its norm reaches theta
+        const bool certified = (t == 0) || phase == 1 || c.best >= theta;
+        if (threadIdx.x == 0) {
+            P->retry = certified ? 0 : 1;
+            P->rest_bits = __double_as_longlong(-1.0);           // the next pass (or catch-up) collects it anew
+            if (!certified) { P->cstar = c.best; P->nretry += 1; }
+            else if (t == 0) P->theta = P->alpha * c.best;       // block start: every norm is exact
+            else if (phase == 1) P->theta = theta;               // what is still skipped is below cstar
+        }
+        if (!certified) return;                  // nothing of step i has been touched: catch-up, then phase 1
+        if (t > 0 && c.second < rest) c.second = rest;           // the runner-up may sit in a skipped segment
     }
     if (threadIdx.x == 32) {
         s_win[0] = c.idx; s_win[1] = c.key; s_win[2] = p_local;
@@ -921,7 +1138,7 @@ qr_panel_kernel(Panel* __restrict__ P, const Cand* __restrict__ cand, int ncand,
     for (int k = lane; k < L; k += 32) {
         double qv = (k == t) ? 1.0 : 0.0;
         for (int a = 0; a <= t; ++a) qv = fma(-s_V[a][k], s_g[a], qv);
-        P->q[k] = qv;
+        P->qs[t][k] = qv;
     }
 }
 
@@ -931,6 +1148,9 @@ struct QrWs {
     Cand* cand;
     Panel* panel;
     double* vn_tmp;
+    double* seg_max;           // [2][nseg]: largest norm of every 64-candidate segment at a block start (ping-pong)
+    unsigned char* seg_skip;   // [nseg]: the segment sits the current block out
+    int64_t nseg;
 };
 
 static int64_t qr_ws_layout(int64_t n, QrWs* w, char* base)
@@ -943,7 +1163,13 @@ static int64_t qr_ws_layout(int64_t n, QrWs* w, char* base)
     char* c = take((int64_t)sizeof(Cand) * QR_NCAND);
     char* d = take((int64_t)sizeof(Panel));
     char* e = take((int64_t)sizeof(double) * npad);
-    if (w) { w->vn1 = (double*)a; w->vn2 = (double*)b; w->cand = (Cand*)c; w->panel = (Panel*)d; w->vn_tmp = (double*)e; }
+    const int64_t nseg = npad / QR_SEG;
+    char* f = take((int64_t)sizeof(double) * 2 * nseg);
+    char* g = take(nseg);
+    if (w) {
+        w->vn1 = (double*)a; w->vn2 = (double*)b; w->cand = (Cand*)c; w->panel = (Panel*)d; w->vn_tmp = (double*)e;
+        w->seg_max = (double*)f; w->seg_skip = (unsigned char*)g; w->nseg = nseg;
+    }
     return off;
 }
 
@@ -965,18 +1191,34 @@ static int64_t gemv_grid(int64_t n)
     int64_t g = ceil_div(basis_tiles(n) * (OMB_TB / 2), GV_THREADS);
     static int per_sm = 0;                     // a whole number of waves of resident CTAs: no straggler CTAs
     if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_gemv_kernel, GV_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_gemv_kernel<GV_PASS>, GV_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
         per_sm *= 2;                           // two whole waves (measured: 2.77 ms vs 2.82 ms for one or three)
     }
     const int64_t cap = (int64_t)sm_count() * per_sm;
     if (g > cap) g = cap;
-    if (g > QR_NCAND) g = QR_NCAND;
+    if (g > QR_NCAND / 2) g = QR_NCAND / 2;    // the upper half of the record array belongs to the catch-up pass
     return g;
 }
 
+// lazy down-dates: theta = alpha * (pivot norm at the block start); <= 0 switches them off.
+// OMB_QR_LAZY overrides the default at load time, omb_qrcp_set_lazy() at run time.
+static double g_lazy_alpha = -1.0;
+static double lazy_alpha()
+{
+    if (g_lazy_alpha < 0.0) {
+        const char* e = getenv("OMB_QR_LAZY");
+        g_lazy_alpha = e ? atof(e) : 0.94;
+        if (!(g_lazy_alpha >= 0.0 && g_lazy_alpha < 1.0)) g_lazy_alpha = 0.0;
+    }
+    return g_lazy_alpha;
+}
+// the segments' ping-pong buffers: block k reads the one its predecessor's apply pass filled
+static double* seg_read(const QrWs& w, int i0, int block) { return w.seg_max + (((i0 / block) + 1) & 1) * w.nseg; }
+static double* seg_write(const QrWs& w, int i0, int block) { return w.seg_max + ((i0 / block) & 1) * w.nseg; }
+
 // norms -> vn1/vn2, position maps, and the step-0 argmax records.  Returns the record count (< 0: error code)
 static int qr_start(const double* d_Ut, int64_t n, int r, int64_t s, const double* d_vn, const QrWs& w, Shard sh,
-                    cudaStream_t st, int* ncand)
+                    double alpha, cudaStream_t st, int* ncand)
 {
     const int sms = sm_count();
     int rc;
@@ -988,11 +1230,13 @@ static int qr_start(const double* d_Ut, int64_t n, int r, int64_t s, const doubl
         if ((rc = check_launch("qr_norms_kernel"))) return rc;
         vn = w.vn_tmp;
     }
-    qr_init_kernel<<<(unsigned)g, 256, 0, st>>>(vn, n, w.vn1, w.vn2, w.panel);
+    qr_init_kernel<<<(unsigned)g, 256, 0, st>>>(vn, n, w.vn1, w.vn2, w.panel, alpha);
     if ((rc = check_launch("qr_init_kernel"))) return rc;
-    // step-0 argmax: a read-only pass over zero rows leaves the norms untouched
+    // step-0 argmax: a read-only pass over zero rows leaves the norms untouched (and the segment
+    // maxima where block 0 reads them)
     const int64_t gv = gemv_grid(n);
-    qr_gemv_kernel<<<(unsigned)gv, GV_THREADS, 0, st>>>(d_Ut, n, r, 0, 0, 0, 0, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+    qr_gemv_kernel<GV_START><<<(unsigned)gv, GV_THREADS, 0, st>>>(d_Ut, n, r, 0, 0, 0, w.panel, w.vn1, w.vn2, s, sh,
+                                                        w.cand, (const double*)nullptr, w.seg_max + w.nseg, w.seg_skip);
     if ((rc = check_launch("qr_gemv_kernel"))) return rc;
     *ncand = (int)gv;
     return 0;
@@ -1019,24 +1263,40 @@ static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t 
         } else {
             // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
             //  tensor-path rounding instead of the oracle's fma order)
-            ApplyMmaFn fm = pick_apply_mma(L, &ng);
+            ApplyMmaFn fm = pick_apply_mma(L, block > 1, &ng);
             g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
             int per_sm = 0;                    // resident CTAs per SM of this instantiation: one full wave
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fm, AM_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
             if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
             if (g > QR_NCAND) g = QR_NCAND;
-            launch_pdl(fm, dim3((unsigned)g), dim3(AM_THREADS), 0, st, src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand);
+            launch_pdl(fm, dim3((unsigned)g), dim3(AM_THREADS), 0, st, src, d_work, n, r, i0, L, t, w.panel, w.vn1, w.vn2, s, sh, w.cand,
+                       seg_write(w, i0, block));
             if ((rc = check_launch("qr_apply_mma_kernel"))) return rc;
         }
         *ncand = (int)g;
     } else {
         const int64_t gv = gemv_grid(n);
-        launch_pdl(qr_gemv_kernel, dim3((unsigned)gv), dim3(GV_THREADS), 0, st, src, n, r, i0, L, t, (t + 1 == L) ? 1 : 0,
-                   (const Panel*)w.panel, w.vn1, w.vn2, s, sh, w.cand);
+        launch_pdl(qr_gemv_kernel<GV_PASS>, dim3((unsigned)gv), dim3(GV_THREADS), 0, st, src, n, r, i0, L, t,
+                   w.panel, w.vn1, w.vn2, s, sh, w.cand, (const double*)seg_read(w, i0, block), seg_write(w, i0, block),
+                   w.seg_skip);
         if ((rc = check_launch("qr_gemv_kernel"))) return rc;
         *ncand = (int)gv;
     }
     return 0;
+}
+
+// lazy down-dates: the conditional catch-up pass after the panel of in-block step t >= 1 (the panel
+// is then launched a second time with phase = 1); both exit at once unless that panel raised `retry`
+static int qr_catchup(const double* src, int64_t n, int r, int64_t s, int block, int i0, int t, const QrWs& w, Shard sh,
+                      cudaStream_t st)
+{
+    int64_t g = gemv_grid(n);
+    const int64_t small = (int64_t)sm_count() * 4;     // few segments join: a small grid keeps the no-op launch cheap
+    if (g > small) g = small;
+    launch_pdl(qr_gemv_kernel<GV_CATCHUP>, dim3((unsigned)g), dim3(GV_THREADS), 0, st, src, n, r, i0, r - i0, t,
+               w.panel, w.vn1, w.vn2, s, sh, w.cand, (const double*)seg_read(w, i0, block), seg_write(w, i0, block),
+               w.seg_skip);
+    return check_launch("qr_gemv_kernel");
 }
 
 static int qr_check(const void* d_Ut, const void* d_work, const void* d_ws, int64_t n, int64_t r, int64_t s, int block)
@@ -1067,15 +1327,19 @@ extern "C" int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, con
     Shard sh;
     sh.n_c_loc = n; sh.n_c = n; sh.cell0 = 0; sh.rank = 0; sh.world = 1;
     int ncand = 0;
-    if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, st, &ncand))) return rc;
+    const double alpha = block > 1 ? lazy_alpha() : 0.0;
+    if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, alpha, st, &ncand))) return rc;
     const double* src = d_Ut;   // trailing matrix as of the block start, rows i0..r-1
     int i0 = 0;
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        launch_pdl(qr_panel_kernel<false>, dim3(1), dim3(PN_THREADS), 0, st, w.panel, (const Cand*)w.cand, ncand, src, ri, i0,
-                   ri - i0, i, t, block == 1 ? 1 : 0, s, index_base, sh, (const double*)nullptr, P2P{nullptr, nullptr, 0},
-                   w.vn1, d_piv, d_rdiag, d_gap);
-        if ((rc = check_launch("qr_panel_kernel"))) return rc;
+        for (int phase = 0; phase < ((alpha > 0.0 && t > 0) ? 2 : 1); ++phase) {
+            if (phase == 1 && (rc = qr_catchup(src, n, ri, s, block, i0, t, w, sh, st))) return rc;
+            launch_pdl(qr_panel_kernel<false>, dim3(1), dim3(PN_THREADS), 0, st, w.panel, (const Cand*)w.cand, ncand, src, ri,
+                       i0, ri - i0, i, t, block == 1 ? 1 : 0, phase, s, index_base, sh, (const double*)nullptr,
+                       P2P{nullptr, nullptr, 0}, w.vn1, d_piv, d_rdiag, d_gap);
+            if ((rc = check_launch("qr_panel_kernel"))) return rc;
+        }
         if (i == (int)s - 1) break;           // no further pivot needed: skip the last pass
         if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
         if (t == block - 1) { src = d_work; i0 = i + 1; }
@@ -1102,7 +1366,8 @@ extern "C" int omb_qrcp_mr_start(const double* d_Ut, int64_t n, int64_t r, int64
     QrWs w;
     qr_ws_layout(n, &w, (char*)d_ws);
     int ncand = 0;
-    return qr_start(d_Ut, n, (int)r, s, d_vn, w, make_shard(n_c_loc, n_c, cell0, rank, world), (cudaStream_t)stream,
+    // the host-gathered exchange steps from the host: no lazy down-dates (their retry is decided on the device)
+    return qr_start(d_Ut, n, (int)r, s, d_vn, w, make_shard(n_c_loc, n_c, cell0, rank, world), 0.0, (cudaStream_t)stream,
                     &ncand);
 }
 
@@ -1138,7 +1403,7 @@ extern "C" int omb_qrcp_mr_step(const double* d_Ut, double* d_work, int64_t n, i
     const int ri = (int)r;
     const int i0 = (int)(i / block) * block, t = (int)i - i0;
     const double* src = i0 == 0 ? d_Ut : d_work;
-    qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, (int)i, t, 0, s, 0, sh,
+    qr_panel_kernel<true><<<1, PN_THREADS, 0, st>>>(w.panel, w.cand, 0, src, ri, i0, ri - i0, (int)i, t, 0, 0, s, 0, sh,
                                                      d_recs, P2P{nullptr, nullptr, 0}, w.vn1, d_piv, d_rdiag, d_gap);
     if ((rc = check_launch("qr_panel_kernel"))) return rc;
     if (i == s - 1) return 0;
@@ -1162,7 +1427,7 @@ extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s,
     int rc = qr_check(d_Ut, d_work, d_ws, n, r, s, block);
     if (rc) return rc;
     OMB_CHECK_ARG(d_peers && d_mine && d_piv && d_rdiag && d_gap, "null pointer");
-    OMB_CHECK_ARG(world >= 2 && world <= 64 && rank >= 0 && rank < world && epoch > 0 && s < 4096, "bad p2p argument");
+    OMB_CHECK_ARG(world >= 2 && world <= 64 && rank >= 0 && rank < world && epoch > 0 && s < 2048, "bad p2p argument");
     cudaStream_t st = (cudaStream_t)stream;
     QrWs w;
     qr_ws_layout(n, &w, (char*)d_ws);
@@ -1172,17 +1437,52 @@ extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s,
     qr_p2p_barrier_kernel<<<1, 64, 0, st>>>(pp, rank, world);
     if ((rc = check_launch("qr_p2p_barrier_kernel"))) return rc;
     int ncand = 0;
-    if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, st, &ncand))) return rc;
+    const double alpha = block > 1 ? lazy_alpha() : 0.0;
+    if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, alpha, st, &ncand))) return rc;
     const double* src = d_Ut;
     int i0 = 0;
     for (int i = 0; i < (int)s; ++i) {
         const int t = i - i0;
-        launch_pdl(qr_panel_kernel<true>, dim3(1), dim3(PN_THREADS), 0, st, w.panel, (const Cand*)w.cand, 0, src, ri, i0, ri - i0,
-                   i, t, 0, s, (int64_t)0, sh, (const double*)nullptr, pp, w.vn1, d_piv, d_rdiag, d_gap);
-        if ((rc = check_launch("qr_panel_kernel"))) return rc;
+        // (the certification uses the GLOBAL winner, so every rank takes the same retry decisions)
+        for (int phase = 0; phase < ((alpha > 0.0 && t > 0) ? 2 : 1); ++phase) {
+            if (phase == 1 && (rc = qr_catchup(src, n, ri, s, block, i0, t, w, sh, st))) return rc;
+            launch_pdl(qr_panel_kernel<true>, dim3(1), dim3(PN_THREADS), 0, st, w.panel, (const Cand*)w.cand, 0, src, ri, i0,
+                       ri - i0, i, t, 0, phase, s, (int64_t)0, sh, (const double*)nullptr, pp, w.vn1, d_piv, d_rdiag, d_gap);
+            if ((rc = check_launch("qr_panel_kernel"))) return rc;
+        }
         if (i == (int)s - 1) break;
         if ((rc = qr_pass(src, d_work, n, ri, s, block, i0, t, w, sh, st, &ncand))) return rc;
         if (t == block - 1) { src = d_work; i0 = i + 1; }
     }
+    return 0;
+}
+
+// ---- lazy down-dates: switch and statistics ----
+// alpha in (0, 1): segments whose largest norm at a block start is below alpha * (pivot norm) sit the
+// block's read-only passes out (exact: see the file header); 0 switches the scheme off.  Returns the
+// previous value.  Process-wide; the default is 0.94 (or $OMB_QR_LAZY).
+extern "C" double omb_qrcp_set_lazy(double alpha)
+{
+    const double prev = lazy_alpha();
+    g_lazy_alpha = (alpha > 0.0 && alpha < 1.0) ? alpha : 0.0;
+    return prev;
+}
+
+// what the read-only passes of the last placement on this workspace actually visited:
+// out[0] = (segment, row) visits (64 candidates x 8 bytes each), out[1] = segment visits,
+// out[2] = catch-up rounds, out[3] = 1 if the lazy scheme was on.  Synchronises the stream.
+extern "C" int omb_qrcp_stats(const void* d_ws, int64_t n, int64_t* out, void* stream)
+{
+    OMB_CHECK_ARG(d_ws && out && n > 0, "bad argument");
+    QrWs w;
+    qr_ws_layout(n, &w, (char*)const_cast<void*>(d_ws));
+    Panel* hp = (Panel*)malloc(sizeof(Panel));
+    OMB_CHECK_ARG(hp != nullptr, "out of host memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(hp, w.panel, sizeof(Panel), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { free(hp); set_error("omb_qrcp_stats: %s", cudaGetErrorString(e)); return (int)e; }
+    out[0] = (int64_t)hp->seg_rows; out[1] = (int64_t)hp->seg_visits; out[2] = hp->nretry; out[3] = hp->lazy;
+    free(hp);
     return 0;
 }

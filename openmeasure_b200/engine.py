@@ -492,6 +492,7 @@ class Engine:
         block = max(1, min(8, int(block)))
         work = torch.empty(self.ntiles, r, TB, dtype=torch.float64, device=self.dev)
         ws = _ws(_lib.load().omb_qrcp_ws_bytes(self.n_loc, r), self.dev)
+        self._qr_ws = ws                              # kept for qr_stats()
         out = torch.empty(3 * s, dtype=torch.float64, device=self.dev)      # one buffer: one D2H for all three
         piv, rdiag, gap = out[:s].view(torch.int64), out[s:2 * s], out[2 * s:]
         self.qr_out = out
@@ -521,6 +522,16 @@ class Engine:
             _lib.call("omb_qrcp_mr_step", _p(self.Ut), _p(work), self.n_loc, r, s, _p(ws), block, i, *sh,
                       _p(recs), _p(piv), _p(rdiag), _p(gap), _stream())
         return piv, rdiag, gap
+
+    def qr_stats(self):
+        """Executed schedule of the last placement's read-only passes (lazy norm down-dates,
+        include/omb200.h `omb_qrcp_stats`): dict(seg_rows, seg_visits, retries, lazy).  Synchronises."""
+        ws = getattr(self, "_qr_ws", None)
+        if ws is None:
+            return None
+        out = (C.c_int64 * 4)()
+        _lib.call("omb_qrcp_stats", _p(ws), self.n_loc, C.cast(out, C.c_void_p), _stream())
+        return {"seg_rows": int(out[0]), "seg_visits": int(out[1]), "retries": int(out[2]), "lazy": bool(out[3])}
 
     # ------------------------------------------------------------------------------------ GEM
     def gem(self, n_sensors, mask_dev=None, xyz_dev=None, d_min=0.0, Ut=None, normal=None, verbose=False):

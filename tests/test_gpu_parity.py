@@ -112,12 +112,20 @@ def test_broken_options_raise_like_reference(torch_cuda):
 # ---------------------------------------------------------------------------------------------
 # K6: pivoted QR kernel vs the C oracle (bitwise, block=1), scipy and the blocked variant
 # ---------------------------------------------------------------------------------------------
-def _gpu_qrcp(torch, Ur, block, s=None):
-    from openmeasure_b200 import engine
+def _gpu_qrcp(torch, Ur, block, s=None, lazy=None, stats=None):
+    """lazy: alpha of the lazy norm down-dates for this call (None: the library default; 0: eager)."""
+    from openmeasure_b200 import _lib, engine
     n, r = Ur.shape
     eng = engine.Engine(torch.zeros(n, 1, dtype=torch.float64, device="cuda"), 1, group=False)
     eng.set_basis_rows(torch.from_numpy(np.ascontiguousarray(Ur)).cuda())
-    piv, rdiag, gap = eng.qrcp(s=s, block=block)
+    prev = _lib.load().omb_qrcp_set_lazy(lazy) if lazy is not None else None
+    try:
+        piv, rdiag, gap = eng.qrcp(s=s, block=block)
+        if stats is not None:
+            stats.update(eng.qr_stats())
+    finally:
+        if prev is not None:
+            _lib.load().omb_qrcp_set_lazy(prev)
     return piv.cpu().numpy(), rdiag.cpu().numpy(), gap.cpu().numpy()
 
 
@@ -158,6 +166,61 @@ def test_qrcp_exact_ties_follow_lapack_order(torch_cuda, block):
         piv, _, gap = _gpu_qrcp(torch_cuda, Ur, block=block)
         np.testing.assert_array_equal(piv, P[:6])
         assert gap.min() == 0.0                                 # the meter reports the ties
+
+
+def _localised_basis(n, r, seed):
+    """Orthonormal n x r basis whose row norms vary by orders of magnitude along the mesh (localised
+    modes, as flame data has them) -- the case in which most segments sit the in-block passes out."""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(0.0, 1.0, n)[:, None]
+    centres, widths = rng.random(r)[None, :], 0.02 + 0.2 * rng.random(r)[None, :]
+    A = np.exp(-((x - centres) / widths) ** 2) * np.cos(2 * np.pi * x * (1 + np.arange(r))[None, :] + rng.random(r))
+    A += 1e-3 * rng.standard_normal((n, r))
+    Q, _ = np.linalg.qr(A)
+    return Q
+
+
+@pytest.mark.parametrize("n,r,block,s", [(50, 5, 2, None), (63, 6, 8, None), (129, 8, 3, None), (2001, 14, 4, None),
+                                         (5000, 40, 8, None), (6000, 100, 8, None), (6000, 100, 3, 37),
+                                         (3001, 128, 6, None), (100000, 24, 5, None), (40000, 130, 8, 64),
+                                         (250000, 40, 8, None)])
+@pytest.mark.parametrize("kind", ["flat", "localised"])
+def test_qrcp_lazy_downdates_match_eager_and_lapack(torch_cuda, n, r, block, s, kind):
+    """Lazy norm down-dates (skipped segments, catch-up rounds, deferred down-dates in the apply pass)
+    pick the pivots of the eager schedule = LAPACK's, for a loose, the default and an over-eager bound."""
+    Ur = _orth(n, r, 3 * n + r) if kind == "flat" else _localised_basis(n, r, n + r)
+    _, R, P = sla.qr(Ur.T, pivoting=True, mode="economic")
+    k = r if s is None else s
+    st0 = {}
+    piv0, rd0, gap0 = _gpu_qrcp(torch_cuda, Ur, block=block, s=s, lazy=0.0, stats=st0)
+    np.testing.assert_array_equal(piv0, P[:k])
+    assert not st0["lazy"] and st0["retries"] == 0
+    retries = 0
+    for alpha in (0.5, 0.94, 0.9995):
+        st = {}
+        piv, rd, gap = _gpu_qrcp(torch_cuda, Ur, block=block, s=s, lazy=alpha, stats=st)
+        np.testing.assert_array_equal(piv, piv0)
+        np.testing.assert_allclose(rd, rd0, rtol=1e-12)
+        np.testing.assert_allclose(np.abs(rd), np.abs(np.diag(R))[:k], rtol=1e-11)
+        assert st["lazy"] and st["seg_rows"] <= st0["seg_rows"] and np.all(gap <= gap0 + 1e-12)
+        retries += st["retries"]
+        if kind == "localised" and n >= 5000 and alpha == 0.94:
+            assert st["seg_rows"] < 0.9 * st0["seg_rows"]        # part of the mesh is never read inside a block
+    if n >= 2001 and block > 2:
+        assert retries > 0                                         # the catch-up path has run
+
+
+def test_qrcp_lazy_ties_and_zero_columns(torch_cuda):
+    """Exact ties across segments and masked (zero) candidates under an over-eager bound."""
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        base = _orth(300, 7, seed)
+        Ur = np.concatenate([base, base[rng.permutation(300)[:170]], 0.0 * base[:90], base], axis=0)
+        _, _, P = sla.qr(Ur.T, pivoting=True, mode="economic")
+        for alpha in (0.94, 0.9995):
+            piv, _, gap = _gpu_qrcp(torch_cuda, Ur, block=4, lazy=alpha)
+            np.testing.assert_array_equal(piv, P[:7])
+            assert gap.min() == 0.0
 
 
 def test_qrcp_partial_steps_and_rank_deficient_columns(torch_cuda):
@@ -447,13 +510,21 @@ def test_two_gpu_peer_memory_parity(torch_cuda):
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in (["20000", "41", "40"], ["6000", "256", "100"]):
+    # OMB_QR_LAZY: the default bound, an over-eager one (a catch-up round and a second exchange at almost
+    # every step) and the eager schedule
+    for extra, lazy in ((["20000", "41", "40"], None), (["6000", "256", "100"], None), (["20000", "41", "40"], "0.9995"),
+                        (["6000", "256", "100"], "0.9995"), (["20000", "41", "40"], "0")):
+        env = dict(os.environ)
+        if lazy is not None:
+            env["OMB_QR_LAZY"] = lazy
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                               "--master-addr", "127.0.0.1", "--master-port", "29533",
                               os.path.join(root, "tools", "mr_check.py")] + extra,
-                             capture_output=True, text=True, timeout=600)
+                             capture_output=True, text=True, timeout=600, env=env)
         assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
         assert "-> OK" in out.stdout
+        if lazy == "0.9995":
+            assert "catch_up_rounds=0 " not in out.stdout
 
 
 # ---------------------------------------------------------------------------------------------

@@ -24,7 +24,10 @@ C = spr.optimal_placement(block=8)
 spr.train(C)
 y = np.zeros((r, 3))
 ok = True
+qst = spr._eng.qr_stats()
 if rank == 0:
+    from openmeasure_b200 import _lib
+    _lib.load().omb_qrcp_set_lazy(0.0)                      # the single-GPU run is the EAGER schedule
     Xg = synth.snapshots(F, n_c, m, r)                      # the whole problem on one GPU
     one = SPR.from_device(Xg, F, group=False)
     one.fit(select_modes="number", n_modes=r)
@@ -35,7 +38,8 @@ if rank == 0:
     dth = float(np.max(np.abs(np.abs(spr.Theta) - np.abs(one.Theta))))
     ok = same_piv and ds < 1e-12 and dth < 1e-9
     print(f"world={world} rows={F*n_c} m={m} r={r} exchange={spr._eng.qr_exchange} p2p_allgathers={getattr(spr._eng.comm, 'p2p_collectives', 0)} "
-          f"pivots_identical={same_piv} max_rel_dsigma={ds:.2e} max_dTheta={dth:.2e} min_gap={spr.qr_gap.min():.2e} -> {'OK' if ok else 'FAIL'}",
+          f"pivots_identical={same_piv} max_rel_dsigma={ds:.2e} max_dTheta={dth:.2e} min_gap={spr.qr_gap.min():.2e} "
+          f"lazy={qst['lazy']} catch_up_rounds={qst['retries']} -> {'OK' if ok else 'FAIL'}",
           flush=True)
 dist.barrier()
 dist.destroy_process_group()
