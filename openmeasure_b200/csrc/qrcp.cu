@@ -536,7 +536,7 @@ constexpr int AM_THREADS = 128;
 constexpr int AM_SV = 10;     // row stride of sV  [row][refl]   : (2p*10 + c) distinct mod 16
 constexpr int AM_ST = 10;     // row stride of sT  [refl][refl']
 
-template <int LG, int NG, bool EXACT>
+template <int LG, int NG>
 __global__ void __launch_bounds__(AM_THREADS)
 qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L, int t,
                     const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
@@ -585,7 +585,7 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
             const int64_t j = j0 + 8 * g + cq;
             const bool owner = (p == tp) && (j < n);
             pv1[g] = owner ? vn1[j] : -1.0;
-            pv2[g] = (owner && !EXACT) ? vn2[j] : 1.0;
+            pv2[g] = owner ? vn2[j] : 1.0;
         }
         double c[LG][NG][2];
 #pragma unroll
@@ -645,12 +645,7 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
                     if (row > t && row < L) stg_stream(out + (8 * G + e) * OMB_TB + 8 * g, c[G][g][e]);
                 }
             }
-        // norms: the lanes holding row t (p == tp) own their column's.  EXACT (the block-closing pass of a
-        // blocked schedule): every column gets its EXACT trailing norm from the registers -- dlaqp2's own
-        // fallback, taken unconditionally, vn2 following as there.  The norms at a block boundary are then
-        // a function of the column alone, whether or not the block's read-only passes visited it (lazy
-        // down-dates), so duplicated candidates stay bit-identical and ties fall as in LAPACK.
-        // !EXACT (a single tall reflector, block == 1): dlaqp2's down-date of row t.
+        // dlaqp2's down-date of row t: the lanes holding row t (p == tp) own their column's norms
         double wmax = -1.0;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -658,7 +653,7 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
             const bool owner = (p == tp) && (j < n);
             double v1 = pv1[g];
             bool redo = false;
-            if (owner && v1 > 0.0) redo = EXACT ? true : downdate(rij[g], v1, pv2[g]);
+            if (owner && v1 > 0.0) redo = downdate(rij[g], v1, pv2[g]);
             if (__any_sync(0xFFFFFFFFu, redo)) {
                 // exact trailing norm: each of the column's 4 lanes sums its rows, then combine
                 double sq = 0.0;
@@ -698,6 +693,180 @@ qr_apply_mma_kernel(const double* __restrict__ src, double* __restrict__ dst, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// block-closing apply pass of a blocked schedule (block > 1): same compact-WY update, and EVERY
+// column leaves with its EXACT trailing norm (sum of squares of the rows written back; dlaqp2's
+// recompute branch taken unconditionally, vn2 following as there).  A norm at a block boundary is
+// then a function of the column alone, whether or not the block's read-only passes visited it
+// (lazy down-dates): duplicated candidates stay bit-identical and ties fall as in LAPACK.
+// The pass is bound by the length of a warp's per-tile chain (loads -> 3 dependent products ->
+// stores -> norms) at 8-12 resident warps per SM, not by the DMMA pipe or by HBM as such (measured:
+// loads alone 6.3 TB/s, stores alone 4.3, the products alone 1.5 ms of a 4.9 ms pass, the sum of the
+// parts = the pass), so the chain is kept short:
+//   * the first product accumulates even and odd row groups separately (half the dependent DMMAs),
+//   * lane p of a column's quad owns column group g = p: the square roots, norm stores and the
+//     candidate bookkeeping of a tile run on all lanes at once instead of NG times on a quarter,
+//   * the NEXT tile's loads are issued right after this tile's stores; the norms are finished
+//     while they fly.
+// ---------------------------------------------------------------------------------------------
+template <int LG, int NG>
+__global__ void __launch_bounds__(AM_THREADS)
+qr_apply_exact_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int r, int i0, int L, int t,
+                      const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
+                      int64_t s_total, Shard sh, Cand* __restrict__ cand, double* __restrict__ seg_w)
+{
+    constexpr int LP = LG * 8;                 // padded rows
+    constexpr int SVT = LP + 2;                // row stride of sVt [refl][row]: == 2 (mod 8)
+    constexpr int WT = 8 * NG;                 // columns per warp tile (divides OMB_TB)
+    __shared__ double sV[LP * AM_SV];
+    __shared__ double sVt[8 * SVT];
+    __shared__ double sT[8 * AM_ST];
+    __shared__ Cand s_c[AM_THREADS / 32];
+    pdl_enter();
+    for (int e = threadIdx.x; e < LP * 8; e += AM_THREADS) {
+        const int k = e >> 3, a = e & 7;
+        const double v = (k < L && a <= t) ? P->V[a][k] : 0.0;
+        sV[k * AM_SV + a] = v;
+        sVt[a * SVT + k] = v;
+    }
+    if (threadIdx.x < 64) {
+        const int a = threadIdx.x >> 3, b = threadIdx.x & 7;
+        sT[a * AM_ST + b] = (a <= b && b <= t) ? P->T[a][b] : 0.0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = lane & 3, cq = lane >> 2;
+    const bool last_row = (t + 1 == L);
+    const bool lazy = P->lazy != 0;
+
+    Cand best = cand_empty();
+    const int64_t nwt = basis_tiles(n) * (OMB_TB / WT);
+    const int64_t wstride = (int64_t)gridDim.x * (AM_THREADS / 32);
+    int64_t wt = (int64_t)blockIdx.x * (AM_THREADS / 32) + warp;
+
+    double c[LG][NG][2];
+    double pv = -1.0;                           // norm of this lane's column (group g = p) of the tile in c
+    // all loads of a warp tile, issued back to back (and the lane's norm, so that the end of the tile
+    // does not add a dependent round trip)
+    auto load_tile = [&](int64_t w) {
+        const int64_t j0 = w * WT;
+        const int64_t tbase = (j0 >> 7) * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + (j0 & (OMB_TB - 1));
+        const double* in = src + tbase + (2 * p) * OMB_TB + cq;
+        const int64_t j = j0 + 8 * p + cq;
+        pv = (p < NG && j < n) ? vn1[j] : -1.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * G + 2 * p + e;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    c[G][g][e] = (row < L) ? ldg_stream(in + (8 * G + e) * OMB_TB + 8 * g) : 0.0;
+            }
+    };
+    bool have = wt < nwt && wt * WT < n;
+    if (have) load_tile(wt);
+    while (have) {
+        const int64_t j0 = wt * WT;
+        // Z^T = C^T V, even and odd row groups on separate accumulators
+        double z[NG][2], zo[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) z[g][0] = z[g][1] = zo[g][0] = zo[g][1] = 0.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double bv = sV[(8 * G + 2 * p + e) * AM_SV + cq];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (G & 1) dmma884(zo[g][0], zo[g][1], c[G][g][e], bv);
+                    else dmma884(z[g][0], z[g][1], c[G][g][e], bv);
+                }
+            }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { z[g][0] += zo[g][0]; z[g][1] += zo[g][1]; }
+        // Z'^T = Z^T T
+        double zp[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) zp[g][0] = zp[g][1] = 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double bv = sT[(2 * p + e) * AM_ST + cq];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) dmma884(zp[g][0], zp[g][1], z[g][e], bv);
+        }
+        // C^T -= Z'^T V^T
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { zp[g][0] = -zp[g][0]; zp[g][1] = -zp[g][1]; }
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double bv = sVt[(2 * p + e) * SVT + 8 * G + cq];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) dmma884(c[G][g][0], c[G][g][1], zp[g][e], bv);
+            }
+        // rows below the block go back to HBM; their squares give the exact trailing norms: each of a
+        // column's 4 lanes sums its rows (two accumulators), the quad combines, lane p keeps column group p
+        const int64_t tbase = (j0 >> 7) * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + (j0 & (OMB_TB - 1));
+        double* out = dst + tbase + (2 * p) * OMB_TB + cq;
+        double sq[NG], sq1[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) sq[g] = sq1[g] = 0.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * G + 2 * p + e;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    if (row > t && row < L) {
+                        stg_stream(out + (8 * G + e) * OMB_TB + 8 * g, c[G][g][e]);
+                        if (e) sq1[g] = fma(c[G][g][e], c[G][g][e], sq1[g]);
+                        else sq[g] = fma(c[G][g][e], c[G][g][e], sq[g]);
+                    }
+            }
+        double mysq = 0.0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            double v = sq[g] + sq1[g];
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            if (p == g) mysq = v;
+        }
+        const int64_t j = j0 + 8 * p + cq;
+        const double pvc = pv;
+        // the next tile's loads fly while this tile's norms are finished
+        wt += wstride;
+        have = wt < nwt && wt * WT < n;
+        if (have) load_tile(wt);
+        double v1 = pvc;                         // < 0: a pivot or no column (p >= NG, j >= n)
+        if (v1 > 0.0) {
+            v1 = last_row ? 0.0 : sqrt(mysq);
+            vn2[j] = v1;
+        }
+        if (v1 >= 0.0) {
+            vn1[j] = v1;
+            cand_push_lazy(best, v1, j, sh, P, s_total);
+        }
+        if (lazy) {
+            // the segment's largest norm at the start of the next block (norms are >= 0 or -1: their
+            // bit patterns order like signed integers)
+            double wmax = v1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = dmax(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+            if (lane == 0)
+                atomicMax(reinterpret_cast<long long*>(seg_w + j0 / QR_SEG), __double_as_longlong(wmax));
+        }
+    }
+    best = cand_block_reduce(best, s_c);
+    if (threadIdx.x == 0) {
+        cand[blockIdx.x] = best;
+        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
+    }
+}
+
 typedef void (*ApplyMmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
                            int64_t, Shard, Cand*, double*);
 
@@ -708,22 +877,22 @@ static ApplyMmaFn pick_apply_mma(int L, bool exact, int* ng)
     const int lg = (L + 7) / 8;
     if (!exact) {
         *ng = lg <= 16 ? 2 : 1;
-        if (lg <= 13) return qr_apply_mma_kernel<13, 2, false>;
-        if (lg <= 16) return qr_apply_mma_kernel<16, 2, false>;
-        if (lg <= 24) return qr_apply_mma_kernel<24, 1, false>;
-        return qr_apply_mma_kernel<32, 1, false>;
+        if (lg <= 13) return qr_apply_mma_kernel<13, 2>;
+        if (lg <= 16) return qr_apply_mma_kernel<16, 2>;
+        if (lg <= 24) return qr_apply_mma_kernel<24, 1>;
+        return qr_apply_mma_kernel<32, 1>;
     }
     switch (lg) {
-#define OMB_AM_CASE(LGV, NGV) case LGV: *ng = NGV; return qr_apply_mma_kernel<LGV, NGV, true>;
+#define OMB_AM_CASE(LGV, NGV) case LGV: *ng = NGV; return qr_apply_exact_kernel<LGV, NGV>;
         OMB_AM_CASE(1, 4) OMB_AM_CASE(2, 4) OMB_AM_CASE(3, 4) OMB_AM_CASE(4, 4) OMB_AM_CASE(5, 4) OMB_AM_CASE(6, 4)
         OMB_AM_CASE(7, 4) OMB_AM_CASE(8, 4) OMB_AM_CASE(9, 2) OMB_AM_CASE(10, 2) OMB_AM_CASE(11, 2)
         OMB_AM_CASE(12, 2) OMB_AM_CASE(13, 2) OMB_AM_CASE(14, 2) OMB_AM_CASE(15, 2) OMB_AM_CASE(16, 2)
 #undef OMB_AM_CASE
         default: break;
     }
-    if (lg <= 24) { *ng = 1; return qr_apply_mma_kernel<24, 1, true>; }
+    if (lg <= 24) { *ng = 1; return qr_apply_exact_kernel<24, 1>; }
     *ng = 1;
-    return qr_apply_mma_kernel<32, 1, true>;
+    return qr_apply_exact_kernel<32, 1>;
 }
 
 // ---------------------------------------------------------------------------------------------
