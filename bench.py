@@ -547,18 +547,17 @@ def run_workload(ctx, w, steps, warmup, peaks, e2e=True, parity=False, brief=Fal
     hbm, fp64 = peaks["hbm_gbs"], peaks["fp64_tflops"]
     n_max = F * shard_cells(n_c, world, 0)[1]          # the largest shard bounds the step
     # the read-only QR passes report what they visited (lazy norm down-dates); the largest count bounds the step
-    qst = spr._eng.qr_stats() or {"seg_rows": 0, "seg_visits": 0, "retries": 0, "lazy": False}
+    qst = spr._eng.qr_stats() or {"seg_rows": 0, "seg_visits": 0, "retries": 0, "lazy": False, "alpha": 0.0}
     qst = {"seg_rows": int(ctx.max_over_ranks(float(qst["seg_rows"]))), "seg_visits": int(ctx.max_over_ranks(float(qst["seg_visits"]))),
-           "retries": int(qst["retries"]), "lazy": bool(qst["lazy"])}
+           "retries": int(qst["retries"]), "lazy": bool(qst["lazy"]), "alpha": float(qst["alpha"])}
     st_roof, comp, qbytes, qlaunch = stage_rooflines(n_max, m, r, stages, ms_per_step, hbm, fp64, peaks, qst)
     qbytes_eager, _ = qrcp_schedule_bytes(n_max, r, r, QR_BLOCK)
-    qr_lazy = {"on": qst["lazy"], "alpha": float(L.omb_qrcp_set_lazy(-1.0)), "catch_up_rounds": qst["retries"],
+    qr_lazy = {"on": qst["lazy"], "alpha": qst["alpha"], "catch_up_rounds": qst["retries"],
                "read_only_pass_bytes": 512 * qst["seg_rows"] + 1536 * qst["seg_visits"],
                "eager_schedule_bytes_per_step": qbytes_eager, "executed_over_eager": qbytes / qbytes_eager,
                "note": "partial column norms only shrink: segments of 64 candidates whose largest norm at a block start is "
                        "below alpha x the pivot norm sit the block's read-only passes out (exact; pivots are those of the "
                        "eager schedule, parity-tested); bytes counted by the kernels"}
-    L.omb_qrcp_set_lazy(qr_lazy["alpha"])
     qr_avg = ctx.max_over_ranks(sum(qr_ms) / max(len(qr_ms), 1))
     achieved = qbytes / (qr_avg * 1e-3) / 1e9 if qr_avg > 0 else 0.0
     traffic, tsrc = None, None

@@ -149,12 +149,16 @@ int64_t omb_qrcp_ws_bytes(int64_t n, int64_t r);
  * alpha * (pivot norm at the block start) sit the block's read-only passes out and take their down-dates
  * in the block-closing pass, which reads them anyway.  A pivot is accepted only if its norm reaches the
  * bound; otherwise the skipped segments that could beat it are brought up to date first (decided on the
- * device) -- the pivots are those of the eager schedule.  alpha in (0, 1), 0 = off; returns the previous
- * value.  Process-wide; default 0.94 or $OMB_QR_LAZY.  Same LAPACK call site (:739). */
+ * device) -- the pivots are those of the eager schedule.  At a block boundary every column's norm is
+ * recomputed exactly from the rows the block-closing pass writes (dlaqp2's recompute branch, taken
+ * unconditionally), so eager and lazy runs hold bit-identical norms, exact ties included.
+ * alpha in (0, 1) fixed, 0 = off, negative = automatic by problem size (the default, or $OMB_QR_LAZY);
+ * returns the previous setting (-1 = automatic).  Process-wide.  Same LAPACK call site (:739). */
 double omb_qrcp_set_lazy(double alpha);
-/* Executed schedule of the last placement on this workspace: out[0] = (segment, row) visits of the
- * read-only passes (512 bytes each), out[1] = their segment visits (64 x 24 bytes of norms each),
- * out[2] = catch-up rounds, out[3] = 1 if the lazy scheme was on.  Synchronises the stream. */
+/* Executed schedule of the last placement on this workspace (6 values): out[0] = (segment, row) visits
+ * of the read-only passes (512 bytes each), out[1] = their segment visits (64 x 24 bytes of norms each),
+ * out[2] = catch-up rounds, out[3] = 1 if the lazy scheme was on, out[4] = its alpha in parts per
+ * million, out[5] = 0.  Synchronises the stream. */
 int omb_qrcp_stats(const void* d_ws, int64_t n, int64_t* out, void* stream);
 int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, const double* d_vn, double* d_work,
              void* d_ws, int block, int64_t index_base, int64_t* d_piv, double* d_rdiag,

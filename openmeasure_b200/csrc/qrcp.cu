@@ -269,7 +269,7 @@ constexpr int QR_SEG = 64;        // candidates per segment
 enum { GV_START = 0, GV_PASS = 1, GV_CATCHUP = 2 };
 
 template <int MODE>
-__global__ void __launch_bounds__(GV_THREADS, 3)
+__global__ void __launch_bounds__(GV_THREADS, MODE == GV_CATCHUP ? 2 : 3)
 qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, int t,
                Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
                int64_t s_total, Shard sh, Cand* __restrict__ cand, const double* __restrict__ seg_r,
@@ -381,21 +381,42 @@ qr_gemv_kernel(const double* __restrict__ src, int64_t n, int r, int i0, int L, 
                     cand_push_lazy(best, v1, jj, sh, P, s_total);
                 }
             } else {
-                // catch-up: the deferred steps one after the other, dlaqp2's down-dates in their order
-                // (rare; the segment's rows come from L2 after the first sweep)
+                // catch-up: one sweep over the segment's rows forms the rows of R of ALL deferred steps (each
+                // accumulator runs over k in the order of the regular pass: same bits), then dlaqp2's
+                // down-dates in step order
                 double v1[2] = {pv1.x, pv1.y}, v2[2] = {pv2.x, pv2.y};
                 bool w2[2] = {false, false};
-                for (int a = 0; a < nq; ++a) {
-                    double y0 = 0.0, y1 = 0.0;
-                    for (int k = 0; k < L; ++k) {
-                        const double2 x = ldg_stream2(col + (int64_t)k * OMB_TB);
-                        y0 = fma(s_q[a][k], x.x, y0);
-                        y1 = fma(s_q[a][k], x.y, y1);
-                    }
+                double y0[NQ], y1[NQ];
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) y0[a] = y1[a] = 0.0;
+                int k = 0;
+                for (; k + 4 <= L; k += 4) {
+                    double2 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = ldg_stream2(col + (int64_t)(k + u) * OMB_TB);
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a)
+                        if (a < nq) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                y0[a] = fma(s_q[a][k + u], x[u].x, y0[a]);
+                                y1[a] = fma(s_q[a][k + u], x[u].y, y1[a]);
+                            }
+                        }
+                }
+                for (; k < L; ++k) {
+                    const double2 x = ldg_stream2(col + (int64_t)k * OMB_TB);
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a)
+                        if (a < nq) { y0[a] = fma(s_q[a][k], x.x, y0[a]); y1[a] = fma(s_q[a][k], x.y, y1[a]); }
+                }
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) {
+                    if (a >= nq) break;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         if (j + e >= n || v1[e] <= 0.0) continue;     // past the end, a pivot, or an exact zero
-                        if (downdate(e ? y1 : y0, v1[e], v2[e])) {
+                        if (downdate(e ? y1[a] : y0[a], v1[e], v2[e])) {
                             v1[e] = (a + 1 == L) ? 0.0 : recompute_norm(col + e, L, a, &P->V[0][0], P->tau);
                             v2[e] = v1[e];
                             w2[e] = true;
@@ -1369,17 +1390,27 @@ static int64_t gemv_grid(int64_t n)
     return g;
 }
 
-// lazy down-dates: theta = alpha * (pivot norm at the block start); <= 0 switches them off.
-// OMB_QR_LAZY overrides the default at load time, omb_qrcp_set_lazy() at run time.
-static double g_lazy_alpha = -1.0;
-static double lazy_alpha()
+// lazy down-dates: theta = alpha * (pivot norm at the block start).  Setting: < 0 automatic (by problem
+// size), 0 off, (0, 1) fixed.  OMB_QR_LAZY overrides the default at load time, omb_qrcp_set_lazy() at run time.
+static double g_lazy_setting = -2.0;           // -2: not read yet
+static double lazy_setting()
 {
-    if (g_lazy_alpha < 0.0) {
+    if (g_lazy_setting == -2.0) {
         const char* e = getenv("OMB_QR_LAZY");
-        g_lazy_alpha = e ? atof(e) : 0.94;
-        if (!(g_lazy_alpha >= 0.0 && g_lazy_alpha < 1.0)) g_lazy_alpha = 0.0;
+        g_lazy_setting = e ? atof(e) : -1.0;
+        if (!(g_lazy_setting < 1.0)) g_lazy_setting = -1.0;
+        if (g_lazy_setting < 0.0) g_lazy_setting = -1.0;
     }
-    return g_lazy_alpha;
+    return g_lazy_setting;
+}
+// A tighter bound skips more segments but fails its certification more often; a catch-up round costs
+// two extra kernels (~25 us) whatever the size, a looser bound costs reads in proportion to n * r.
+// Measured optima: 0.90 at 1.65M x 40, 0.92-0.94 at 2M x 100, 0.94-0.95 at 16.2M x 100.
+static double lazy_alpha(int64_t n, int r)
+{
+    const double a = lazy_setting();
+    if (a >= 0.0) return a;
+    return (double)n * r < 1.0e8 ? 0.90 : 0.94;
 }
 // the segments' ping-pong buffers: block k reads the one its predecessor's apply pass filled
 static double* seg_read(const QrWs& w, int i0, int block) { return w.seg_max + (((i0 / block) + 1) & 1) * w.nseg; }
@@ -1496,7 +1527,7 @@ extern "C" int omb_qrcp(const double* d_Ut, int64_t n, int64_t r, int64_t s, con
     Shard sh;
     sh.n_c_loc = n; sh.n_c = n; sh.cell0 = 0; sh.rank = 0; sh.world = 1;
     int ncand = 0;
-    const double alpha = block > 1 ? lazy_alpha() : 0.0;
+    const double alpha = block > 1 ? lazy_alpha(n, ri) : 0.0;
     if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, alpha, st, &ncand))) return rc;
     const double* src = d_Ut;   // trailing matrix as of the block start, rows i0..r-1
     int i0 = 0;
@@ -1606,7 +1637,7 @@ extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s,
     qr_p2p_barrier_kernel<<<1, 64, 0, st>>>(pp, rank, world);
     if ((rc = check_launch("qr_p2p_barrier_kernel"))) return rc;
     int ncand = 0;
-    const double alpha = block > 1 ? lazy_alpha() : 0.0;
+    const double alpha = block > 1 ? lazy_alpha(n, ri) : 0.0;
     if ((rc = qr_start(d_Ut, n, ri, s, d_vn, w, sh, alpha, st, &ncand))) return rc;
     const double* src = d_Ut;
     int i0 = 0;
@@ -1628,18 +1659,20 @@ extern "C" int omb_qrcp_p2p(const double* d_Ut, int64_t n, int64_t r, int64_t s,
 
 // ---- lazy down-dates: switch and statistics ----
 // alpha in (0, 1): segments whose largest norm at a block start is below alpha * (pivot norm) sit the
-// block's read-only passes out (exact: see the file header); 0 switches the scheme off.  Returns the
-// previous value.  Process-wide; the default is 0.94 (or $OMB_QR_LAZY).
+// block's read-only passes out (exact: see the file header); 0 switches the scheme off; negative =
+// automatic (by problem size; the default, or $OMB_QR_LAZY).  Returns the previous setting (-1 =
+// automatic).  Process-wide.
 extern "C" double omb_qrcp_set_lazy(double alpha)
 {
-    const double prev = lazy_alpha();
-    g_lazy_alpha = (alpha > 0.0 && alpha < 1.0) ? alpha : 0.0;
+    const double prev = lazy_setting();
+    g_lazy_setting = alpha < 0.0 ? -1.0 : ((alpha > 0.0 && alpha < 1.0) ? alpha : 0.0);
     return prev;
 }
 
 // what the read-only passes of the last placement on this workspace actually visited:
 // out[0] = (segment, row) visits (64 candidates x 8 bytes each), out[1] = segment visits,
-// out[2] = catch-up rounds, out[3] = 1 if the lazy scheme was on.  Synchronises the stream.
+// out[2] = catch-up rounds, out[3] = 1 if the lazy scheme was on, out[4] = its alpha in parts per
+// million, out[5] = 0 (reserved).  Synchronises the stream.
 extern "C" int omb_qrcp_stats(const void* d_ws, int64_t n, int64_t* out, void* stream)
 {
     OMB_CHECK_ARG(d_ws && out && n > 0, "bad argument");
@@ -1652,6 +1685,7 @@ extern "C" int omb_qrcp_stats(const void* d_ws, int64_t n, int64_t* out, void* s
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { free(hp); set_error("omb_qrcp_stats: %s", cudaGetErrorString(e)); return (int)e; }
     out[0] = (int64_t)hp->seg_rows; out[1] = (int64_t)hp->seg_visits; out[2] = hp->nretry; out[3] = hp->lazy;
+    out[4] = (int64_t)(hp->alpha * 1.0e6 + 0.5); out[5] = 0;
     free(hp);
     return 0;
 }

@@ -525,13 +525,14 @@ class Engine:
 
     def qr_stats(self):
         """Executed schedule of the last placement's read-only passes (lazy norm down-dates,
-        include/omb200.h `omb_qrcp_stats`): dict(seg_rows, seg_visits, retries, lazy).  Synchronises."""
+        include/omb200.h `omb_qrcp_stats`): dict(seg_rows, seg_visits, retries, lazy, alpha).  Synchronises."""
         ws = getattr(self, "_qr_ws", None)
         if ws is None:
             return None
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 6)()
         _lib.call("omb_qrcp_stats", _p(ws), self.n_loc, C.cast(out, C.c_void_p), _stream())
-        return {"seg_rows": int(out[0]), "seg_visits": int(out[1]), "retries": int(out[2]), "lazy": bool(out[3])}
+        return {"seg_rows": int(out[0]), "seg_visits": int(out[1]), "retries": int(out[2]), "lazy": bool(out[3]),
+                "alpha": out[4] / 1.0e6}
 
     # ------------------------------------------------------------------------------------ GEM
     def gem(self, n_sensors, mask_dev=None, xyz_dev=None, d_min=0.0, Ut=None, normal=None, verbose=False):
