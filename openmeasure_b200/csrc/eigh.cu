@@ -274,12 +274,17 @@ __global__ void __launch_bounds__(256)
 pod_weights_kernel(const double* __restrict__ w, const double* __restrict__ V, int m, double rel_floor,
                    double* __restrict__ S, double* __restrict__ W)
 {
+    // thread = mode q (its square root and reciprocal are formed once), CTAs stride over the rows of V
     const double s0 = sqrt(fmax(w[0], 0.0));
-    for (int e = threadIdx.x; e < m * m; e += 256) {
-        const int q = e % m;
+    for (int q = threadIdx.x; q < m; q += 256) {
         const double sq = sqrt(fmax(w[q], 0.0));
-        W[e] = (sq > s0 * rel_floor) ? V[e] * (1.0 / sq) : 0.0;
-        if (e < m) S[e] = sqrt(fmax(w[e], 0.0));
+        const bool live = sq > s0 * rel_floor;
+        const double inv = live ? 1.0 / sq : 0.0;
+        if (blockIdx.x == 0) S[q] = sq;
+        for (int row = blockIdx.x; row < m; row += gridDim.x) {
+            const int64_t e = (int64_t)row * m + q;
+            W[e] = live ? V[e] * inv : 0.0;
+        }
     }
 }
 
@@ -304,6 +309,7 @@ extern "C" int omb_pod_weights(const double* d_w, const double* d_V, int64_t m, 
     using namespace omb;
     OMB_CHECK_ARG(d_w && d_V && d_S && d_W, "null pointer");
     OMB_CHECK_ARG(m >= 1 && m <= 4096, "m must be in [1, 4096]");
-    pod_weights_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_w, d_V, (int)m, rel_floor, d_S, d_W);
+    const int grid = (int)(m < 2 * (int64_t)sm_count() ? m : 2 * (int64_t)sm_count());
+    pod_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_w, d_V, (int)m, rel_floor, d_S, d_W);
     return check_launch("pod_weights_kernel");
 }
