@@ -102,6 +102,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+// ---- TMA tensor copies (2-D tiled tensor maps, cuTensorMapEncodeTiled on the host).  SASS: UTMALDG / UTMASTG ----
+// global -> shared: box of the map at coordinates (c0 = innermost, c1), completing on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* sdst, const void* tmap, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* ssrc)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(ssrc)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the sources of all committed bulk stores have been read (their shared memory may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have been written to global memory
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8).  SASS: DMMA.8x8x4.
 //   a  = A[lane/4][lane%4],  b = B[lane%4][lane/4],  c0/c1 = C[lane/4][2*(lane%4) + {0,1}]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)

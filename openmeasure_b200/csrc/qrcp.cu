@@ -42,6 +42,7 @@
 // eager runs therefore hold bit-identical norms at every decision, exact ties included.
 // The decisions depend on the data only (identical on every rank of a row-sharded run).
 #include "common.cuh"
+#include <cuda.h>      // CUtensorMap (types only: the encoder comes through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include "../../include/omb200.h"
 
@@ -888,6 +889,235 @@ qr_apply_exact_kernel(const double* __restrict__ src, double* __restrict__ dst, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same block-closing pass with its loads on the TMA engine (6 <= ceil(L/8) <= 13: shorter blocks stay on the register-staged kernel, whose 32-candidate warp tiles amortise the per-tile work better).
+// ncu on qr_apply_exact_kernel: 40 % of the warps' samples wait for the tile's loads, and the LSU data
+// pipe moves ONE 32-byte sector per wavefront for its fragment-shaped accesses (4 row segments of 64
+// bytes per instruction) -- 848 M wavefronts for 25 GB, the pipe 63 % busy.  Here a warp tile (16
+// candidates x L rows = rows of 128 bytes, 1 KB apart in HBM) arrives as ONE tensor copy:
+//   * every warp runs its own pipeline of TWO landing stages -- no CTA-wide synchronisation: lane 0
+//     issues the tensor load of the warp's tile k + 2 (mbarrier completion) as soon as tile k has been
+//     pulled into the registers, so two tiles per warp (26 KB) are in flight while one is worked on;
+//   * the stages use the 128-byte swizzle of the tensor map (16-byte chunk index XOR row mod 8): a
+//     fragment read -- 4 rows x 4 candidates per half-warp -- hits 8 distinct chunks, i.e. one
+//     conflict-free wavefront per half-warp (unswizzled rows of 128 bytes would be a 4-way conflict);
+//   * the results leave from the registers (streaming stores, fire and forget).
+// 8 warps x 2 stages x 13 KB = 208 KB of shared memory at L = 100: one CTA per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int AT_WARPS = 8;
+constexpr int AT_THREADS = AT_WARPS * 32;
+constexpr int AT_WT = 16;                      // candidates per warp tile (two DMMA column groups)
+
+// byte offset of (row, byte column) in a stage of 128-byte rows under the 128-byte swizzle
+__device__ __forceinline__ int at_swz(int row, int colb) { return row * 128 + (colb ^ ((row & 7) << 4)); }
+
+template <int LG>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+qr_apply_tma_kernel(const __grid_constant__ CUtensorMap map_in, double* __restrict__ dst, int64_t n, int r,
+                    int i0, int L, int t, const Panel* __restrict__ P, double* __restrict__ vn1, double* __restrict__ vn2,
+                    int64_t s_total, Shard sh, Cand* __restrict__ cand, double* __restrict__ seg_w)
+{
+    constexpr int NG = 2;
+    constexpr int LP = LG * 8;                 // padded rows
+    constexpr int SVT = LP + 2;                // row stride of sVt [refl][row]: == 2 (mod 8)
+    constexpr int STAGE = LP * 128;            // bytes per stage (a multiple of 1 KB: the swizzle atom)
+    __shared__ double sV[LP * AM_SV];
+    __shared__ double sVt[8 * SVT];
+    __shared__ double sT[8 * AM_ST];
+    __shared__ Cand s_c[AT_WARPS];
+    __shared__ uint64_t s_bar[AT_WARPS][2];
+    extern __shared__ __align__(1024) unsigned char s_stages[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* my_st = s_stages + (size_t)warp * (2 * STAGE);
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_enter();
+    for (int e = threadIdx.x; e < LP * 8; e += AT_THREADS) {
+        const int k = e >> 3, a = e & 7;
+        const double v = (k < L && a <= t) ? P->V[a][k] : 0.0;
+        sV[k * AM_SV + a] = v;
+        sVt[a * SVT + k] = v;
+    }
+    if (threadIdx.x < 64) {
+        const int a = threadIdx.x >> 3, b = threadIdx.x & 7;
+        sT[a * AM_ST + b] = (a <= b && b <= t) ? P->T[a][b] : 0.0;
+    }
+    fence_proxy_async();                       // the barrier inits are visible to the TMA unit
+    __syncthreads();
+
+    const int p = lane & 3, cq = lane >> 2;
+    const bool last_row = (t + 1 == L);
+    const bool lazy = P->lazy != 0;
+    const uint32_t tx_bytes = (uint32_t)L * 128u;
+
+    Cand best = cand_empty();
+    const int64_t nwt = basis_tiles(n) * (OMB_TB / AT_WT);
+    const int64_t wstride = (int64_t)gridDim.x * AT_WARPS;
+    int64_t wt = (int64_t)blockIdx.x * AT_WARPS + warp;
+    auto valid = [&](int64_t w) { return w < nwt && w * AT_WT < n; };
+    // tensor load of warp tile w into stage s (lane 0)
+    auto issue_tile = [&](int64_t w, int s) {
+        if (lane == 0) {
+            mbar_expect_tx(&s_bar[warp][s], tx_bytes);
+            tma_load_2d(my_st + s * STAGE, &map_in, (int)((w & 7) * AT_WT), (int)((w >> 3) * r + i0), &s_bar[warp][s]);
+        }
+    };
+    if (valid(wt)) issue_tile(wt, 0);
+    if (valid(wt + wstride)) issue_tile(wt + wstride, 1);
+    uint32_t phases = 0u;                       // bit s: parity of stage s's barrier
+    int s = 0;
+    while (valid(wt)) {
+        const int64_t j0 = wt * AT_WT;
+        const int64_t j = j0 + 8 * p + cq;
+        // this lane's column of the tile (group g = p): its norm, fetched before the wait
+        const double pv = (p < NG && j < n) ? vn1[j] : -1.0;
+        mbar_wait(&s_bar[warp][s], (phases >> s) & 1u);
+        phases ^= 1u << s;
+        const unsigned char* in_st = my_st + s * STAGE;
+        double c[LG][NG][2];
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * G + 2 * p + e;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    c[G][g][e] = (row < L) ? *reinterpret_cast<const double*>(in_st + at_swz(row, (8 * g + cq) * 8)) : 0.0;
+            }
+        // Z^T = C^T V, even and odd row groups on separate accumulators
+        double z[NG][2], zo[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) z[g][0] = z[g][1] = zo[g][0] = zo[g][1] = 0.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double bv = sV[(8 * G + 2 * p + e) * AM_SV + cq];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (G & 1) dmma884(zo[g][0], zo[g][1], c[G][g][e], bv);
+                    else dmma884(z[g][0], z[g][1], c[G][g][e], bv);
+                }
+            }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { z[g][0] += zo[g][0]; z[g][1] += zo[g][1]; }
+        // every staged element has been consumed by a DMMA of its lane: the stage takes the tile after next
+        __syncwarp();
+        if (valid(wt + 2 * wstride)) issue_tile(wt + 2 * wstride, s);
+        // Z'^T = Z^T T
+        double zp[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) zp[g][0] = zp[g][1] = 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double bv = sT[(2 * p + e) * AM_ST + cq];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) dmma884(zp[g][0], zp[g][1], z[g][e], bv);
+        }
+        // C^T -= Z'^T V^T
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { zp[g][0] = -zp[g][0]; zp[g][1] = -zp[g][1]; }
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double bv = sVt[(2 * p + e) * SVT + 8 * G + cq];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) dmma884(c[G][g][0], c[G][g][1], zp[g][e], bv);
+            }
+        // rows below the block go back to HBM; their squares give the exact trailing norms
+        const int64_t tbase = (j0 >> 7) * ((int64_t)r * OMB_TB) + (int64_t)i0 * OMB_TB + (j0 & (OMB_TB - 1));
+        double* out = dst + tbase + (2 * p) * OMB_TB + cq;
+        double sq[NG], sq1[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) sq[g] = sq1[g] = 0.0;
+#pragma unroll
+        for (int G = 0; G < LG; ++G)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * G + 2 * p + e;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    if (row > t && row < L) {
+                        stg_stream(out + (8 * G + e) * OMB_TB + 8 * g, c[G][g][e]);
+                        if (e) sq1[g] = fma(c[G][g][e], c[G][g][e], sq1[g]);
+                        else sq[g] = fma(c[G][g][e], c[G][g][e], sq[g]);
+                    }
+            }
+        double mysq = 0.0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            double v = sq[g] + sq1[g];
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            if (p == g) mysq = v;
+        }
+        double v1 = pv;                          // < 0: a pivot or no column (p >= NG, j >= n)
+        if (v1 > 0.0) {
+            v1 = last_row ? 0.0 : sqrt(mysq);
+            vn2[j] = v1;
+        }
+        if (v1 >= 0.0) {
+            vn1[j] = v1;
+            cand_push_lazy(best, v1, j, sh, P, s_total);
+        }
+        if (lazy) {
+            double wmax = v1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = dmax(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+            if (lane == 0)
+                atomicMax(reinterpret_cast<long long*>(seg_w + j0 / QR_SEG), __double_as_longlong(wmax));
+        }
+        wt += wstride;
+        s ^= 1;
+    }
+    best = cand_block_reduce(best, s_c);
+    if (threadIdx.x == 0) {
+        cand[blockIdx.x] = best;
+        if (blockIdx.x == 0) const_cast<Panel*>(P)->ncand = (int)gridDim.x;
+    }
+}
+
+typedef void (*ApplyTmaFn)(const CUtensorMap, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
+                           int64_t, Shard, Cand*, double*);
+static ApplyTmaFn pick_apply_tma(int L)
+{
+    static int lg_min = -1;                    // ($OMB_QR_APPLY_TMA_MIN: shortest block, in groups of 8 rows, that takes this kernel)
+    if (lg_min < 0) { const char* e = getenv("OMB_QR_APPLY_TMA_MIN"); lg_min = e ? atoi(e) : 6; }
+    if ((L + 7) / 8 < lg_min) return nullptr;
+    switch ((L + 7) / 8) {
+#define OMB_AT_CASE(LGV) case LGV: return qr_apply_tma_kernel<LGV>;
+        OMB_AT_CASE(1) OMB_AT_CASE(2) OMB_AT_CASE(3) OMB_AT_CASE(4) OMB_AT_CASE(5) OMB_AT_CASE(6) OMB_AT_CASE(7)
+        OMB_AT_CASE(8) OMB_AT_CASE(9) OMB_AT_CASE(10) OMB_AT_CASE(11) OMB_AT_CASE(12) OMB_AT_CASE(13)
+#undef OMB_AT_CASE
+        default: return nullptr;
+    }
+}
+
+// 2-D view of a tiled basis (tiles * r rows of 128 candidates) with a box of 16 candidates x box_rows rows
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int basis_tensor_map(CUtensorMap* m, const double* base, int64_t ntiles, int r, int box_rows)
+{
+    static TmapEncodeFn enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) return -1;
+        enc = (TmapEncodeFn)fp;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)OMB_TB, (cuuint64_t)(ntiles * r)};
+    const cuuint64_t strides[1] = {(cuuint64_t)OMB_TB * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)AT_WT, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+}
+
 typedef void (*ApplyMmaFn)(const double*, double*, int64_t, int, int, int, int, const Panel*, double*, double*,
                            int64_t, Shard, Cand*, double*);
 
@@ -1463,6 +1693,25 @@ static int qr_pass(const double* src, double* d_work, int64_t n, int r, int64_t 
         } else {
             // (block == 1 with more than QR_LREG trailing rows also lands here: same algorithm,
             //  tensor-path rounding instead of the oracle's fma order)
+            // the block-closing pass on the TMA engine ($OMB_QR_APPLY_TMA=0: the register-staged kernel)
+            static int use_tma = -1;
+            if (use_tma < 0) { const char* e = getenv("OMB_QR_APPLY_TMA"); use_tma = e ? atoi(e) : 1; }
+            ApplyTmaFn ft = (block > 1 && use_tma && (((uintptr_t)src) & 127) == 0) ? pick_apply_tma(L) : nullptr;
+            CUtensorMap map_in;
+            if (ft && basis_tensor_map(&map_in, src, ntiles, r, L)) ft = nullptr;
+            if (ft) {
+                const int lp = ((L + 7) / 8) * 8;
+                const size_t stage = (size_t)AT_WARPS * 2 * lp * 128;
+                OMB_CUDA(cudaFuncSetAttribute(ft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+                g = sms;                       // one CTA of 8 independent warp pipelines per SM
+                const int64_t need = ceil_div(ntiles * (OMB_TB / AT_WT), AT_WARPS);
+                if (g > need) g = need;
+                launch_pdl(ft, dim3((unsigned)g), dim3(AT_THREADS), stage, st, map_in, d_work, n, r, i0, L, t, (const Panel*)w.panel,
+                           w.vn1, w.vn2, s, sh, w.cand, seg_write(w, i0, block));
+                if ((rc = check_launch("qr_apply_tma_kernel"))) return rc;
+                *ncand = (int)g;
+                return 0;
+            }
             ApplyMmaFn fm = pick_apply_mma(L, block > 1, &ng);
             g = ceil_div(ntiles * (OMB_TB / (8 * ng)), AM_THREADS / 32);
             int per_sm = 0;                    // resident CTAs per SM of this instantiation: one full wave
