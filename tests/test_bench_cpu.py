@@ -28,6 +28,26 @@ def test_qrcp_schedule_bytes_counts_the_executed_passes():
     assert t8 <= min(b.qrcp_schedule_bytes(n, r, r, k)[0] for k in (2, 4, 16, 32)) * 1.02
 
 
+def test_qrcp_schedule_bytes_of_a_lazy_run_charge_what_the_passes_visited():
+    """Lazy norm down-dates: the block-closing apply passes touch every column, the read-only passes only the
+    segments the kernels counted (omb_qrcp_stats): 512 bytes per (segment, row), 1.5 KB of norms per visit."""
+    b = _bench()
+    n, r, blk = 64 * 1000, 40, 8
+    eager, launches = b.qrcp_schedule_bytes(n, r, r, blk)
+    nseg = n // 64
+    # every segment visited by every read-only pass = the eager schedule
+    rows = sum((r - (i // blk) * blk) * nseg for i in range(r - 1) if i % blk != blk - 1)
+    visits = sum(nseg for i in range(r - 1) if i % blk != blk - 1)
+    full, l2 = b.qrcp_schedule_bytes(n, r, r, blk, {"lazy": True, "seg_rows": rows, "seg_visits": visits})
+    assert (full, l2) == (eager, launches)
+    # nothing visited: only the apply passes (and the step-0 argmax) are left
+    none, _ = b.qrcp_schedule_bytes(n, r, r, blk, {"lazy": True, "seg_rows": 0, "seg_visits": 0})
+    apply_only = 8 * n + sum(8 * n * (r - i0) + 24 * n + 8 * n * (r - i0 - blk) for i0 in range(0, r - blk, blk))
+    assert none == apply_only and none < 0.3 * eager
+    # stats of an eager run (lazy flag off) are ignored
+    assert b.qrcp_schedule_bytes(n, r, r, blk, {"lazy": False, "seg_rows": 1, "seg_visits": 1})[0] == eager
+
+
 def test_stage_rooflines_use_algorithmic_work():
     b = _bench()
     n, m, r = 16_200_000, 256, 100

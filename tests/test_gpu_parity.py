@@ -210,6 +210,34 @@ def test_qrcp_lazy_downdates_match_eager_and_lapack(torch_cuda, n, r, block, s, 
         assert retries > 0                                         # the catch-up path has run
 
 
+def test_qrcp_apply_kernels_agree_bitwise(torch_cuda, tmp_path):
+    """The block-closing apply pass has two implementations (tensor-copy / TMA landing stages for 41..104
+    trailing rows, register-staged otherwise): same products, same norm arithmetic -> the same bits.  The
+    switch is read once per process, so the register-staged run happens in a child process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    Ur = _localised_basis(20000, 100, 5)
+    np.save(tmp_path / "Ur.npy", Ur)
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+            "from openmeasure_b200 import engine\n"
+            "Ur = np.load(%r)\n"
+            "eng = engine.Engine(torch.zeros(Ur.shape[0], 1, dtype=torch.float64, device='cuda'), 1, group=False)\n"
+            "eng.set_basis_rows(torch.from_numpy(Ur).cuda())\n"
+            "piv, rd, gap = eng.qrcp(block=8)\n"
+            "np.savez(%r, piv=piv.cpu().numpy(), rd=rd.cpu().numpy(), gap=gap.cpu().numpy())\n"
+            % (root, str(tmp_path / "Ur.npy"), str(tmp_path / "reg.npz")))
+    env = dict(os.environ, OMB_QR_APPLY_TMA="0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    reg = np.load(tmp_path / "reg.npz")
+    piv, rd, gap = _gpu_qrcp(torch_cuda, Ur, block=8)
+    np.testing.assert_array_equal(piv, reg["piv"])
+    np.testing.assert_array_equal(rd, reg["rd"])
+    np.testing.assert_array_equal(gap, reg["gap"])
+    _, _, P = sla.qr(Ur.T, pivoting=True, mode="economic")
+    np.testing.assert_array_equal(piv, P[:100])
+
+
 def test_qrcp_lazy_ties_and_zero_columns(torch_cuda):
     """Exact ties across segments and masked (zero) candidates under an over-eager bound."""
     for seed in range(4):
