@@ -19,7 +19,9 @@
 //                          write the rows below the block, norms (block > 1: exact), argmax.
 //                            block == 1: dlarf arithmetic in registers, the very fma sequence of
 //                                        oracle/csrc/oracle.c -> bit-identical to dlaqp2;
-//                            block  > 1: compact WY on the FP64 tensor path (DMMA.8x8x4).
+//                            block  > 1: compact WY on the FP64 tensor path (DMMA.8x8x4); with 41 .. 104
+//                                        trailing rows the tiles arrive as TMA tensor copies
+//                                        (qr_apply_tma_kernel), otherwise through registers.
 //
 // block > 1 moves ~ (1 + 1/block)/2 of the bytes of the unblocked algorithm; pivots are identical
 // on non-degenerate inputs (the degeneracy meter d_gap reports how close any decision was).
