@@ -1,11 +1,13 @@
-"""Summarise an `ncu --csv` launch list: per-kernel count, total/avg duration, DRAM bytes, GB/s."""
+"""Summarise an `ncu --csv` launch list (plain or .gz): per-kernel count, total/avg duration, DRAM bytes, GB/s."""
 import collections
 import csv
+import gzip
 import sys
 
 
 def main(fn, skip_first=0):
-    rows = list(csv.reader(l for l in open(fn) if l.startswith('"')))
+    op = gzip.open if fn.endswith(".gz") else open
+    rows = list(csv.reader(l for l in op(fn, "rt") if l.startswith('"')))
     hdr = rows[0]
     ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
     per = collections.OrderedDict()
